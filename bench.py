@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point Laplacian steps/s of the B200 filter path vs the HBM roofline.
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg3] [--impl reference]
+
+One "step" = one pass of the hot path (a whole filter call: prepare, n_steps Chebyshev steps,
+finalize) over one synthetic batch.  Default workload (BASELINE.json north_star headline, SURVEY
+8(d) cfg3): Gaussian IRREGULAR_WITH_LAND filter, filter_scale 36 / dx_min 0.9 -> n_steps 44, on a
+62 x 2400 x 3600 fp64 POP 0.1-degree field (NaN on land).  Units are grid-point Laplacian steps
+(points x n_steps).
+
+  value     device-resident throughput: inputs already in HBM, CUDA events around K filter calls
+  e2e       the same through the public API Filter.apply() with pinned HOST buffers (H2D + D2H inside)
+  roofline  dominant kernel (the mid-recurrence step kernel): algorithmic bytes (B_alg = 5w*ncomp + C/nb
+            per pt-step) / CUDA-event duration per launch, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the numpy oracle port (oracle/np_oracle.py) on the host cores, bounded sample
+
+Multi-GPU (torchrun, one rank per GPU): the batch dimension shards with no data-path collective;
+every rank filters its own 62-level field (weak scaling); NCCL is used for the barrier and the
+max-over-ranks of the timings only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grid_point_laplacian_steps_per_sec"
+UNIT = "pt-steps/s"
+
+
+# ------------------------------------------------------------------------------------------ workloads
+def build_workload(name, nb, rank=0):
+    from oracle import fixtures  # deterministic synthetic inputs only (no compute)
+
+    if name == "cfg3":
+        cfg = fixtures.cfg3(nb=nb or 62)
+    elif name == "cfg3f32":
+        cfg = fixtures.cfg3(nb=nb or 62, dtype=np.float32)
+    elif name == "cfg3taper":
+        cfg = fixtures.cfg3(nb=nb or 62, gaussian=False)
+    elif name == "cfg2":
+        cfg = fixtures.cfg2(nb=nb or 365)
+    elif name == "cfg4":
+        cfg = fixtures.cfg4(nb=nb or None)
+    elif name == "cfg5":
+        cfg = fixtures.cfg5()
+    elif name == "cfg1":
+        cfg = fixtures.cfg1()
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    if rank:  # weak scaling: every rank filters a different field of the same shape
+        cfg["fields"] = tuple(f * f.dtype.type(1.0 + 0.01 * rank) for f in cfg["fields"])
+    return cfg
+
+
+def c_bytes_per_point(grid_type, w):
+    """Coefficient-plane bytes per grid point (C in B_alg = 5 w ncomp + C/nb)."""
+    return {"REGULAR": 0, "REGULAR_AREA_WEIGHTED": 0, "REGULAR_WITH_LAND": 1, "REGULAR_WITH_LAND_AREA_WEIGHTED": 1,
+            "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED": 1, "IRREGULAR_WITH_LAND": 3 * w, "MOM5U": 3 * w,
+            "MOM5T": 3 * w, "TRIPOLAR_POP_WITH_LAND": 3 * w, "VECTOR_B_GRID": 8 * w, "VECTOR_C_GRID": 14 * w}[grid_type]
+
+
+def workload_descr(cfg, n_steps):
+    f0 = cfg["fields"][0]
+    return {"workload": f"{cfg['name']}: {cfg['grid_type']} {cfg['filter_args']['filter_shape']} "
+                        f"filter_scale={cfg['filter_args']['filter_scale']:g} dx_min={cfg['filter_args']['dx_min']:g} "
+                        f"n_steps={n_steps} field={'x'.join(str(s) for s in f0.shape)} {f0.dtype}",
+            "grid_type": cfg["grid_type"], "n_steps": int(n_steps), "shape": list(f0.shape),
+            "l2_policy": "inputs larger than L2 (no flush needed)" if f0.nbytes > 2 * 126e6 else
+                         "L2 flushed between timed iterations"}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+_CPU = {}
+
+
+def _cpu_worker(args):
+    """One worker = one 2-D slice through the oracle's recurrence (numpy, single-threaded ufuncs)."""
+    from oracle import np_oracle
+
+    idx, n_steps = args
+    cfg = _CPU["cfg"]
+    fa = dict(cfg["filter_args"], n_steps=n_steps)
+    fields = tuple(f[idx] if f.ndim == 3 else f for f in cfg["fields"])
+    t0 = time.perf_counter()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np_oracle.apply_filter(cfg["grid_type"], cfg["grid_vars"], fields, **fa)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(cfg, n_steps_sample=8, max_workers=32, repeats=1):
+    """Oracle port on the host cores: `workers` processes x 1 slice each x n_steps_sample steps."""
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0))
+    f0 = cfg["fields"][0]
+    nslices = f0.shape[0] if f0.ndim == 3 else 1
+    workers = max(1, min(cores, max_workers, nslices))
+    _CPU["cfg"] = cfg
+    pts = f0.shape[-1] * f0.shape[-2]
+    best = None
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(i, n_steps_sample) for i in range(workers)])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    value = workers * pts * n_steps_sample / best
+    return {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": f"{workers} slice(s) of {f0.shape[-2]}x{f0.shape[-1]} ({cfg['grid_type']}, {f0.dtype}) x "
+                      f"n_steps={n_steps_sample} (per-step cost is constant), one process per slice, "
+                      f"numpy oracle port; host has {cores} usable cores", "seconds": best}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out, _ = self.proc.communicate(timeout=10)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from gcm_filters_b200 import Filter, FilterShape, GridType, _cabi, engine
+    from gcm_filters_b200.filter import _shift_scale
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = build_workload(args.workload, args.nb, rank)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(cfg)  # before any CUDA work in this process' children (fork)
+
+    fa = dict(cfg["filter_args"])
+    fa["filter_shape"] = FilterShape[fa["filter_shape"]]
+    flt = Filter(grid_type=GridType[cfg["grid_type"]], grid_vars=cfg["grid_vars"], **fa)
+    n_steps = int(flt.n_steps)
+    lap = flt.laplacian
+    lib = _cabi.get_library()
+    spec = flt.filter_spec
+    c = _shift_scale(spec, lap)
+
+    fields = cfg["fields"]
+    shape = fields[0].shape
+    ny, nx = shape[-2:]
+    nb = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+    w = fields[0].dtype.itemsize
+    ncomp = len(fields)
+    units_per_step = nb * ny * nx * n_steps  # grid-point Laplacian steps in one filter call
+
+    # host buffers (pinned) for the end-to-end leg, device-resident copies for the kernel leg
+    host_in = [torch.from_numpy(np.ascontiguousarray(f)).pin_memory() for f in fields]
+    host_out = [torch.empty_like(h).pin_memory() for h in host_in]
+    dev_in = [h.to(dev).reshape(nb, ny, nx) for h in host_in]
+    dev_out = [torch.empty_like(d) for d in dev_in]
+    small = dev_in[0].numel() * w <= 2 * 126e6
+    flush = torch.empty(int(300e6), dtype=torch.uint8, device=dev) if small else None
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    stream = torch.cuda.current_stream(dev)
+
+    # ---- leg 1: device-resident filter calls -------------------------------------------------
+    for _ in range(args.warmup):
+        engine.filter_device(lap, spec.p, c, dev_in, dev_out)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        if flush is not None:
+            flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        engine.filter_device(lap, spec.p, c, dev_in, dev_out)
+        ev[k][1].record(stream)
+    barrier()
+    launches = lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dev_ms = max_over_ranks(dev_ms)
+    value = world * units_per_step * args.steps / (dev_ms * 1e-3)
+
+    # ---- leg 2: end to end through Filter.apply with pinned host buffers ------------------------
+    def e2e_once():
+        if ncomp == 1:
+            flt.apply(host_in[0], dims=["y", "x"], out=host_out[0])
+        else:
+            flt.apply_to_vector(host_in[0], host_in[1], dims=["y", "x"], out=host_out)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_once()
+    barrier()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_once()  # returns after the D2H copy of the result has completed
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * units_per_step * e2e_steps / e2e_s
+    h2d = sum(h.numel() * h.element_size() for h in host_in)
+    d2h = sum(h.numel() * h.element_size() for h in host_out)
+
+    # ---- leg 3: per-launch duration of the dominant kernel (mid-recurrence step) ----------------
+    plan = engine.device_plan(lap, local, fields[0].dtype, ny, nx)
+    plan.set_filter(spec.p, c)
+    ws = engine.workspace(dev, lib.workspace_bytes(plan.handle, nb))
+    bufbytes = lib.workspace_bytes(plan.handle, nb) // (2 * ncomp)
+    spec_of = lambda ts: [(t.data_ptr(), nx, ny * nx) for t in ts]
+    A = [(ws.data_ptr() + k * bufbytes, nx, ny * nx) for k in range(ncomp)]
+    B = [(ws.data_ptr() + (ncomp + k) * bufbytes, nx, ny * nx) for k in range(ncomp)]
+    sptr = stream.cuda_stream
+    mid_ms = []
+    area = cfg["grid_type"] in ("REGULAR_AREA_WEIGHTED", "REGULAR_WITH_LAND_AREA_WEIGHTED",
+                                "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED")
+    for rep in range(max(1, min(args.steps, 3))):
+        X = spec_of(dev_in)
+        if area:
+            lib.prepare(plan.handle, nb, X, B, sptr)
+            X = B
+        lib.cheb_step(plan.handle, nb, 1, X, None, A, spec_of(dev_out), sptr)
+        T1, T2 = A, X
+        for i in range(2, n_steps + 1):
+            D = B if (i == 2 and not area) else T2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            lib.cheb_step(plan.handle, nb, i, T1, T2, D, spec_of(dev_out), sptr)
+            e1.record(stream)
+            if i < n_steps:
+                mid_ms.append((e0, e1))
+            T2, T1 = T1, D
+    torch.cuda.synchronize(dev)
+    mid = float(np.mean([a.elapsed_time(b) for a, b in mid_ms])) if mid_ms else float("nan")
+    b_alg = 5 * w * ncomp + c_bytes_per_point(cfg["grid_type"], w) / nb
+    peak, peak_src = measured_hbm_peak()
+    achieved = b_alg * nb * ny * nx / (mid * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "step_kernel<MODE_MID> (one Chebyshev step)",
+                "ms_per_launch": mid, "algorithmic_bytes_per_pt_step": b_alg, "peak_source": peak_src}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(prof):
+        try:
+            with open(prof) as fh:
+                roofline["traffic"] = json.load(fh).get(args.workload)
+        except Exception:
+            pass
+
+    total_launches = int(sum_over_ranks(launches))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if w == 8 else "f32", "data": "synthetic (numpy PCG64, SURVEY 8(d))",
+        "config": dict(workload_descr(cfg, n_steps), sharding="batch slabs, one full field per GPU, no collective"),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "Filter.apply(pinned host tensor, out=pinned host tensor)"},
+        "gpu_launches": total_launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def reference_arm(args):
+    """The reference is pure Python/numpy and cannot travel to the GPU box; its CPU implementation of
+    the path is timed through the oracle port (bit-identical to it, tests/test_oracle.py) on all host
+    cores, on a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = build_workload(args.workload, args.nb)
+    from oracle import np_oracle
+    fa = cfg["filter_args"]
+    n_steps = np_oracle.resolve_n_steps(fa["filter_scale"], fa["dx_min"], fa["filter_shape"])
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(cfg, n_steps_sample=3)
+    t_all, res = 0.0, None
+    steps = max(1, min(args.steps, 3))
+    for _ in range(steps):
+        res = cpu_baseline(cfg)
+        t_all += res["seconds"]
+    f0 = cfg["fields"][0]
+    units = res["cores"] * f0.shape[-1] * f0.shape[-2] * 8
+    value = units * steps / t_all
+    res["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_all / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if f0.dtype.itemsize == 8 else "f32",
+        "data": "synthetic (numpy PCG64, SURVEY 8(d))", "config": workload_descr(cfg, n_steps),
+        "cpu_baseline": res,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--nb", type=int, default=0, help="override the batch size (levels / time steps)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

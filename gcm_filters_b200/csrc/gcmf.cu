@@ -1,0 +1,436 @@
+// gcmf.cu -- libgcmf.so: C ABI (include/gcmf.h) + the one-step Chebyshev/Laplacian kernels.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// (see gcm_filters_b200/build.py).  No torch, no Python.h: plain CUDA runtime.
+//
+// The same file builds the TEST-ONLY host emulator (tests/hostemu/build.sh: g++ -DGCMF_HOSTEMU -x c++):
+// there every "launch" is a plain loop over (b, j, i0) on host pointers, so the C ABI, the step
+// sequencing and the index handling can be checked on a machine without a GPU.  The emulator is
+// never built into, nor loaded by, the product (gcm_filters_b200 loads libgcmf.so only).
+#ifdef GCMF_HOSTEMU
+#define GCMF_HD inline
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gcmf.h"
+#include "gcmf_internal.h"
+#include "gcmf_stencils.cuh"
+
+using namespace gcmf;
+
+// ------------------------------------------------------------------ errors / bookkeeping
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+int gcmf_set_error(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+void gcmf_count_launch(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#ifdef GCMF_HOSTEMU
+typedef void* cudaStream_t;
+#define CUDA_TRY(expr) do { } while (0)
+#else
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return gcmf_set_error(GCMF_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));     \
+    } while (0)
+#endif
+
+extern "C" int gcmf_version(void) { return GCMF_VERSION; }
+#ifdef GCMF_HOSTEMU
+extern "C" int gcmf_sm_arch(void) { return 0; }  // 0 = host emulator (tests only)
+#else
+extern "C" int gcmf_sm_arch(void) { return 100; }
+#endif
+extern "C" const char* gcmf_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t gcmf_launch_count(void) { return g_launches.load(); }
+
+static int n_planes_required(int op, int flags) {
+    switch (op) {
+        case GCMF_OP_REGULAR5: return (flags & GCMF_FLAG_AREA) ? 2 : ((flags & GCMF_FLAG_MASK) ? 1 : 0);
+        case GCMF_OP_FLUX: return 3;
+        case GCMF_OP_VECTOR_B: return 8;
+        case GCMF_OP_VECTOR_C: return 14;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------ plan
+extern "C" int gcmf_plan_create(const gcmf_plan_desc* d, gcmf_plan** out) {
+    if (!d || !out) return gcmf_set_error(GCMF_EINVAL, "null argument");
+    if (d->op < 0 || d->op > GCMF_OP_VECTOR_C) return gcmf_set_error(GCMF_EINVAL, "unknown op %d", d->op);
+    if (d->dtype != GCMF_F32 && d->dtype != GCMF_F64) return gcmf_set_error(GCMF_EINVAL, "unknown dtype %d", d->dtype);
+    if (d->ny < 1 || d->nx < 2) return gcmf_set_error(GCMF_EINVAL, "grid %d x %d too small", d->ny, d->nx);
+    if ((d->flags & GCMF_FLAG_MASK) && d->op != GCMF_OP_REGULAR5)
+        return gcmf_set_error(GCMF_EINVAL, "GCMF_FLAG_MASK is only meaningful for GCMF_OP_REGULAR5");
+    if ((d->flags & GCMF_FLAG_AREA) && d->op != GCMF_OP_REGULAR5)
+        return gcmf_set_error(GCMF_EINVAL, "GCMF_FLAG_AREA is only meaningful for GCMF_OP_REGULAR5");
+    if ((d->flags & (GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S)) && d->op >= GCMF_OP_VECTOR_B)
+        return gcmf_set_error(GCMF_EINVAL, "the tripolar fold is not defined for the vector operators");
+    if ((d->flags & GCMF_FLAG_FOLD_N) && (d->flags & GCMF_FLAG_WRAP_Y) && !(d->flags & GCMF_FLAG_CUT_S))
+        return gcmf_set_error(GCMF_EINVAL, "a folded grid that wraps in y needs GCMF_FLAG_CUT_S");
+#ifndef GCMF_HOSTEMU
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (d->device < 0 || d->device >= ndev) return gcmf_set_error(GCMF_EINVAL, "device %d not present", d->device);
+#endif
+    gcmf_plan* p = new gcmf_plan();
+    p->desc = *d;
+    p->ncomp = d->op >= GCMF_OP_VECTOR_B ? 2 : 1;
+    p->n_planes = n_planes_required(d->op, d->flags);
+    memset(p->plane, 0, sizeof p->plane);
+    p->n_steps = 0;
+    p->c = 0.0;
+#ifdef GCMF_HOSTEMU
+    p->sm_count = 1;
+#else
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+    p->sm_count = prop.multiProcessorCount;
+#endif
+    *out = p;
+    return GCMF_OK;
+}
+
+extern "C" int gcmf_plan_destroy(gcmf_plan* p) {
+    delete p;
+    return GCMF_OK;
+}
+
+extern "C" int gcmf_plan_set_plane(gcmf_plan* p, int slot, const void* dptr, int64_t pitch, int64_t bstride,
+                                   int32_t plane_nb) {
+    if (!p) return gcmf_set_error(GCMF_EINVAL, "null plan");
+    if (slot < 0 || slot >= p->n_planes)
+        return gcmf_set_error(GCMF_EINVAL, "plane slot %d out of range (op needs %d planes)", slot, p->n_planes);
+    if (!dptr || pitch < p->desc.nx || plane_nb < 1)
+        return gcmf_set_error(GCMF_EINVAL, "bad plane (ptr %p pitch %lld nb %d)", dptr, (long long)pitch, plane_nb);
+    p->plane[slot] = PlaneRef{dptr, pitch, bstride, plane_nb};
+    return GCMF_OK;
+}
+
+extern "C" int gcmf_plan_set_filter(gcmf_plan* p, int32_t n_steps, const double* coef, double c) {
+    if (!p || !coef) return gcmf_set_error(GCMF_EINVAL, "null argument");
+    if (n_steps < 2) return gcmf_set_error(GCMF_EINVAL, "n_steps must be >= 2 (got %d)", n_steps);
+    p->n_steps = n_steps;
+    p->p.assign(coef, coef + n_steps + 1);
+    p->c = c;
+    return GCMF_OK;
+}
+
+static int check_planes(const gcmf_plan* p) {
+    for (int s = 0; s < p->n_planes; ++s) {
+        if (p->desc.op == GCMF_OP_REGULAR5 && s == 0 && !(p->desc.flags & GCMF_FLAG_MASK)) continue;
+        if (!p->plane[s].p) return gcmf_set_error(GCMF_ESTATE, "coefficient plane %d has not been set", s);
+    }
+    if (p->desc.op == GCMF_OP_VECTOR_C)
+        for (int s = 1; s < 14; ++s)
+            if (p->plane[s].pitch != p->plane[0].pitch)
+                return gcmf_set_error(GCMF_EINVAL, "GCMF_OP_VECTOR_C planes must share one pitch");
+    return GCMF_OK;
+}
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t buffer_bytes(const gcmf_plan* p, int64_t nb) {
+    const size_t w = p->desc.dtype == GCMF_F64 ? 8 : 4;
+    return round_up((size_t)nb * p->desc.ny * p->desc.nx * w, 256);
+}
+
+extern "C" int gcmf_workspace_bytes(const gcmf_plan* p, int64_t nb, size_t* bytes) {
+    if (!p || !bytes || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
+    *bytes = 2 * (size_t)p->ncomp * buffer_bytes(p, nb);
+    return GCMF_OK;
+}
+
+// ------------------------------------------------------------------ kernels
+constexpr int BX = 32, BY = 8;
+
+// 1-D grid; block id decodes as (x-block fastest, then batch, then row band): every batch slice
+// of a row band is swept before the next band, so the band's coefficient-plane rows are read
+// from HBM once and hit in L2 for the other nb-1 slices.
+#ifndef GCMF_HOSTEMU
+template <typename T, int VX, class OP, int MODE>
+__global__ void __launch_bounds__(BX* BY) step_kernel(const __grid_constant__ StepParams<T> P, int nxb) {
+    int64_t bid = blockIdx.x;
+    const int xb = (int)(bid % nxb);
+    bid /= nxb;
+    const int b = (int)(bid % P.nb);
+    const int yb = (int)(bid / P.nb);
+    const int i0 = (xb * BX + threadIdx.x) * VX;
+    const int j = yb * BY + threadIdx.y;
+    if (i0 < P.g.nx && j < P.g.ny) step_body<T, VX, OP, MODE>(P, b, j, i0);
+}
+
+template <typename T>
+__global__ void prepare_kernel(const T* in, int64_t in_pitch, int64_t in_bs, T* out, int64_t out_pitch, int64_t out_bs,
+                               PlaneRef area, int ny, int nx, int64_t nb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= nx) return;
+    for (int64_t b = blockIdx.z; b < nb; b += gridDim.z) {
+        const T* a = plane_base<T>(area, (int)b);
+        prepare_body<T>(in, out, a, b * in_bs + (int64_t)j * in_pitch + i, b * out_bs + (int64_t)j * out_pitch + i,
+                        (int64_t)j * area.pitch + i);
+    }
+}
+
+#endif  // !GCMF_HOSTEMU
+
+template <typename T, int VX, class OP, int MODE>
+static int launch_step(const StepParams<T>& P, cudaStream_t st) {
+#ifdef GCMF_HOSTEMU
+    (void)st;
+    for (int64_t b = 0; b < P.nb; ++b)
+        for (int j = 0; j < P.g.ny; ++j)
+            for (int i0 = 0; i0 < P.g.nx; i0 += VX) step_body<T, VX, OP, MODE>(P, (int)b, j, i0);
+    gcmf_count_launch(1);
+    return GCMF_OK;
+#else
+    const int nxb = (P.g.nx + BX * VX - 1) / (BX * VX);
+    const int nyb = (P.g.ny + BY - 1) / BY;
+    const int64_t nblk = (int64_t)nxb * nyb * P.nb;
+    if (nblk > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "grid too large (%lld blocks)", (long long)nblk);
+    step_kernel<T, VX, OP, MODE><<<(unsigned)nblk, dim3(BX, BY), 0, st>>>(P, nxb);
+    gcmf_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCMF_OK;
+#endif
+}
+
+template <typename T, int VX, class OP>
+static int launch_mode(const StepParams<T>& P, int mode, cudaStream_t st) {
+    switch (mode) {
+        case MODE_LAP: return launch_step<T, VX, OP, MODE_LAP>(P, st);
+        case MODE_FIRST: return launch_step<T, VX, OP, MODE_FIRST>(P, st);
+        case MODE_MID: return launch_step<T, VX, OP, MODE_MID>(P, st);
+        case MODE_LAST: return launch_step<T, VX, OP, MODE_LAST>(P, st);
+    }
+    return gcmf_set_error(GCMF_EINVAL, "bad mode %d", mode);
+}
+
+template <typename T> struct VecWidth;
+template <> struct VecWidth<double> { static constexpr int value = 2; };
+template <> struct VecWidth<float> { static constexpr int value = 4; };
+
+template <typename T, int VX>
+static int launch_op(const gcmf_plan* pl, const StepParams<T>& P, int mode, cudaStream_t st) {
+    switch (pl->desc.op) {
+        case GCMF_OP_REGULAR5:
+            if (pl->desc.flags & GCMF_FLAG_MASK) return launch_mode<T, VX, OpRegular5<T, VX, true>>(P, mode, st);
+            return launch_mode<T, VX, OpRegular5<T, VX, false>>(P, mode, st);
+        case GCMF_OP_FLUX: return launch_mode<T, VX, OpFlux<T, VX>>(P, mode, st);
+        case GCMF_OP_VECTOR_B: return launch_mode<T, VX, OpVectorB<T, VX>>(P, mode, st);
+        case GCMF_OP_VECTOR_C: return launch_mode<T, 1, OpVectorC<T, 1>>(P, mode, st);
+    }
+    return gcmf_set_error(GCMF_EINVAL, "bad op");
+}
+
+static bool aligned(const void* p, int64_t pitch, int64_t bstride, int vx, size_t elem) {
+    return ((uintptr_t)p % (vx * elem) == 0) && pitch % vx == 0 && bstride % vx == 0;
+}
+
+// can every array of this launch be accessed with VX-wide vectors?
+template <typename T> static bool can_vectorize(const gcmf_plan* pl, const StepParams<T>& P, int mode) {
+    const int vx = VecWidth<T>::value;
+    if (P.g.nx % vx) return false;
+    const int nc = pl->ncomp;
+    for (int k = 0; k < nc; ++k) {
+        if (!aligned(P.t1[k].p, P.t1[k].pitch, P.t1[k].bstride, vx, sizeof(T))) return false;
+        if (mode != MODE_LAST && !aligned(P.t0[k].p, P.t0[k].pitch, P.t0[k].bstride, vx, sizeof(T))) return false;
+        if (mode >= MODE_MID && !aligned(P.t2[k].p, P.t2[k].pitch, P.t2[k].bstride, vx, sizeof(T))) return false;
+        if (mode != MODE_LAP && !aligned(P.bar[k].p, P.bar[k].pitch, P.bar[k].bstride, vx, sizeof(T))) return false;
+    }
+    for (int s = 0; s < pl->n_planes; ++s) {
+        if (!P.plane[s].p) continue;
+        const bool is_mask = pl->desc.op == GCMF_OP_REGULAR5 && s == 0;
+        if (!aligned(P.plane[s].p, P.plane[s].pitch, P.plane[s].bstride, vx, is_mask ? 1 : sizeof(T))) return false;
+    }
+    return true;
+}
+
+template <typename T>
+static int run_step_t(const gcmf_plan* pl, int64_t nb, int mode, const gcmf_field* t1, const gcmf_field* t2,
+                      const gcmf_field* t0, const gcmf_field* bar, double p0, double p1, cudaStream_t st) {
+    StepParams<T> P;
+    memset(&P, 0, sizeof P);
+    P.g.ny = pl->desc.ny;
+    P.g.nx = pl->desc.nx;
+    P.g.flags = pl->desc.flags;
+    for (int s = 0; s < pl->n_planes; ++s) P.plane[s] = pl->plane[s];
+    for (int k = 0; k < pl->ncomp; ++k) {
+        if (t1) P.t1[k] = FieldRef<const T>{(const T*)t1[k].ptr, t1[k].pitch, t1[k].bstride};
+        if (t2) P.t2[k] = FieldRef<const T>{(const T*)t2[k].ptr, t2[k].pitch, t2[k].bstride};
+        if (t0) P.t0[k] = FieldRef<T>{(T*)t0[k].ptr, t0[k].pitch, t0[k].bstride};
+        if (bar) P.bar[k] = FieldRef<T>{(T*)bar[k].ptr, bar[k].pitch, bar[k].bstride};
+    }
+    P.c = pl->c;
+    P.p0 = p0;
+    P.p1 = p1;
+    P.nb = nb;
+    if (can_vectorize<T>(pl, P, mode)) return launch_op<T, VecWidth<T>::value>(pl, P, mode, st);
+    return launch_op<T, 1>(pl, P, mode, st);
+}
+
+static int run_step(const gcmf_plan* pl, int64_t nb, int mode, const gcmf_field* t1, const gcmf_field* t2,
+                    const gcmf_field* t0, const gcmf_field* bar, double p0, double p1, cudaStream_t st) {
+    if (pl->desc.dtype == GCMF_F64) return run_step_t<double>(pl, nb, mode, t1, t2, t0, bar, p0, p1, st);
+    return run_step_t<float>(pl, nb, mode, t1, t2, t0, bar, p0, p1, st);
+}
+
+static int check_fields(const gcmf_plan* p, const gcmf_field* f, const char* what) {
+    if (!f) return gcmf_set_error(GCMF_EINVAL, "%s: null field array", what);
+    for (int k = 0; k < p->ncomp; ++k)
+        if (!f[k].ptr || f[k].pitch < p->desc.nx)
+            return gcmf_set_error(GCMF_EINVAL, "%s[%d]: bad field (ptr %p pitch %lld)", what, k, f[k].ptr,
+                                  (long long)f[k].pitch);
+    return GCMF_OK;
+}
+
+#define TRY(expr)                    \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != GCMF_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------ public compute entry points
+extern "C" int gcmf_laplacian(gcmf_plan* p, int64_t nb, const gcmf_field* in, const gcmf_field* out, void* stream) {
+    if (!p || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
+    TRY(check_planes(p));
+    TRY(check_fields(p, in, "in"));
+    TRY(check_fields(p, out, "out"));
+    CUDA_TRY(cudaSetDevice(p->desc.device));
+    return run_step(p, nb, MODE_LAP, in, nullptr, out, nullptr, 0.0, 0.0, (cudaStream_t)stream);
+}
+
+extern "C" int gcmf_prepare(gcmf_plan* p, int64_t nb, const gcmf_field* in, const gcmf_field* out, void* stream) {
+    if (!p || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
+    TRY(check_fields(p, in, "in"));
+    TRY(check_fields(p, out, "out"));
+    CUDA_TRY(cudaSetDevice(p->desc.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t w = p->desc.dtype == GCMF_F64 ? 8 : 4;
+    const int ny = p->desc.ny, nx = p->desc.nx;
+#ifdef GCMF_HOSTEMU
+    (void)st;
+    for (int k = 0; k < p->ncomp; ++k)
+        for (int64_t b = 0; b < nb; ++b)
+            for (int j = 0; j < ny; ++j)
+                for (int i = 0; i < nx; ++i) {
+                    const int64_t ii = b * in[k].bstride + (int64_t)j * in[k].pitch + i;
+                    const int64_t oi = b * out[k].bstride + (int64_t)j * out[k].pitch + i;
+                    if (!(p->desc.flags & GCMF_FLAG_AREA)) {
+                        memcpy((char*)out[k].ptr + oi * w, (const char*)in[k].ptr + ii * w, w);
+                    } else if (p->desc.dtype == GCMF_F64) {
+                        prepare_body<double>((const double*)in[k].ptr, (double*)out[k].ptr,
+                                             plane_base<double>(p->plane[1], (int)b), ii, oi,
+                                             (int64_t)j * p->plane[1].pitch + i);
+                    } else {
+                        prepare_body<float>((const float*)in[k].ptr, (float*)out[k].ptr,
+                                            plane_base<float>(p->plane[1], (int)b), ii, oi,
+                                            (int64_t)j * p->plane[1].pitch + i);
+                    }
+                }
+    return GCMF_OK;
+#else
+    for (int k = 0; k < p->ncomp; ++k) {
+        if (!(p->desc.flags & GCMF_FLAG_AREA)) {
+            for (int64_t b = 0; b < nb; ++b)  // plain strided copy
+                CUDA_TRY(cudaMemcpy2DAsync((char*)out[k].ptr + b * out[k].bstride * w, out[k].pitch * w,
+                                           (const char*)in[k].ptr + b * in[k].bstride * w, in[k].pitch * w,
+                                           (size_t)nx * w, ny, cudaMemcpyDeviceToDevice, st));
+            continue;
+        }
+        TRY(check_planes(p));
+        dim3 blk(256), grd((nx + 255) / 256, ny, (unsigned)(nb < 64 ? nb : 64));
+        if (p->desc.dtype == GCMF_F64)
+            prepare_kernel<double><<<grd, blk, 0, st>>>((const double*)in[k].ptr, in[k].pitch, in[k].bstride,
+                                                        (double*)out[k].ptr, out[k].pitch, out[k].bstride,
+                                                        p->plane[1], ny, nx, nb);
+        else
+            prepare_kernel<float><<<grd, blk, 0, st>>>((const float*)in[k].ptr, in[k].pitch, in[k].bstride,
+                                                       (float*)out[k].ptr, out[k].pitch, out[k].bstride, p->plane[1],
+                                                       ny, nx, nb);
+        gcmf_count_launch(1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return GCMF_OK;
+#endif
+}
+
+extern "C" int gcmf_cheb_step(gcmf_plan* p, int64_t nb, int32_t step, const gcmf_field* t1_in, const gcmf_field* t2,
+                              const gcmf_field* t0_out, const gcmf_field* bar, void* stream) {
+    if (!p || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
+    if (p->n_steps < 2) return gcmf_set_error(GCMF_ESTATE, "gcmf_plan_set_filter has not been called");
+    if (step < 1 || step > p->n_steps) return gcmf_set_error(GCMF_EINVAL, "step %d outside 1..%d", step, p->n_steps);
+    TRY(check_planes(p));
+    TRY(check_fields(p, t1_in, "t1_in"));
+    TRY(check_fields(p, bar, "bar"));
+    const int mode = step == 1 ? MODE_FIRST : (step == p->n_steps ? MODE_LAST : MODE_MID);
+    if (mode != MODE_FIRST) TRY(check_fields(p, t2, "t2"));
+    if (mode != MODE_LAST) {
+        TRY(check_fields(p, t0_out, "t0_out"));
+        for (int k = 0; k < p->ncomp; ++k)
+            if (t0_out[k].ptr == t1_in[k].ptr) return gcmf_set_error(GCMF_EINVAL, "t0_out must not alias t1_in");
+    }
+    CUDA_TRY(cudaSetDevice(p->desc.device));
+    const double p0 = p->p[0], p1 = mode == MODE_FIRST ? p->p[1] : p->p[step];
+    return run_step(p, nb, mode, t1_in, t2, t0_out, bar, p0, p1, (cudaStream_t)stream);
+}
+
+extern "C" int gcmf_filter(gcmf_plan* p, int64_t nb, const gcmf_field* in, const gcmf_field* out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    if (!p || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
+    if (p->n_steps < 2) return gcmf_set_error(GCMF_ESTATE, "gcmf_plan_set_filter has not been called");
+    TRY(check_planes(p));
+    TRY(check_fields(p, in, "in"));
+    TRY(check_fields(p, out, "out"));
+    size_t need = 0;
+    TRY(gcmf_workspace_bytes(p, nb, &need));
+    if (!workspace || workspace_bytes < need)
+        return gcmf_set_error(GCMF_EINVAL, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    if ((uintptr_t)workspace % 256) return gcmf_set_error(GCMF_EINVAL, "workspace must be 256-byte aligned");
+    for (int k = 0; k < p->ncomp; ++k)
+        if (in[k].ptr == out[k].ptr) return gcmf_set_error(GCMF_EINVAL, "out must not alias in");
+    const int nc = p->ncomp;
+    const int64_t pitch = p->desc.nx, bs = (int64_t)p->desc.ny * p->desc.nx;
+    const size_t bb = buffer_bytes(p, nb);
+    gcmf_field A[2], B[2], X[2];
+    for (int k = 0; k < nc; ++k) {
+        A[k] = gcmf_field{(char*)workspace + (size_t)k * bb, pitch, bs};
+        B[k] = gcmf_field{(char*)workspace + (size_t)(nc + k) * bb, pitch, bs};
+        X[k] = in[k];
+    }
+    const bool area = (p->desc.flags & GCMF_FLAG_AREA) != 0;
+    if (area) {  // x = f * area, materialised once in B (kernels.py:100-101)
+        TRY(gcmf_prepare(p, nb, in, B, stream));
+        for (int k = 0; k < nc; ++k) X[k] = B[k];
+    }
+    // step 1: T1 = A(x) -> A ; bar = p0 x + p1 T1 -> out        (filter.py:191-195)
+    TRY(gcmf_cheb_step(p, nb, 1, X, nullptr, A, out, stream));
+    gcmf_field T1[2], T2[2];
+    for (int k = 0; k < nc; ++k) { T1[k] = A[k]; T2[k] = X[k]; }
+    for (int i = 2; i <= p->n_steps; ++i) {  // filter.py:196-206; pointer rotation replaces the two .copy()
+        gcmf_field D[2];
+        for (int k = 0; k < nc; ++k) D[k] = (i == 2 && !area) ? B[k] : T2[k];  // never write the user's input
+        TRY(gcmf_cheb_step(p, nb, i, T1, T2, D, out, stream));
+        for (int k = 0; k < nc; ++k) { T2[k] = T1[k]; T1[k] = D[k]; }
+    }
+    return GCMF_OK;
+}

@@ -1,0 +1,22 @@
+// gcmf_internal.h -- private definitions shared by the translation units of libgcmf.so.
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/gcmf.h"
+#include "gcmf_stencils.cuh"
+
+struct gcmf_plan {
+    gcmf_plan_desc desc;
+    int ncomp;
+    int n_planes;
+    gcmf::PlaneRef plane[gcmf::MAX_PLANES];
+    int32_t n_steps;
+    std::vector<double> p;  // Chebyshev coefficients p[0..n_steps]
+    double c;
+    int sm_count;
+};
+
+int gcmf_set_error(int code, const char* fmt, ...);
+void gcmf_count_launch(int64_t n);

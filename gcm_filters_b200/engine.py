@@ -1,0 +1,255 @@
+"""Execution engine: device plans, buffers and streams around the C ABI of libgcmf.so.
+
+PyTorch is used for plumbing only -- device memory (tensors own every pointer handed to the
+library), pinned staging, streams.  All arithmetic of the hot path happens inside libgcmf.so.
+"""
+import threading
+
+import numpy as np
+
+from . import _cabi
+
+_DT = {np.dtype(np.float32): _cabi.GCMF_F32, np.dtype(np.float64): _cabi.GCMF_F64}
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise _cabi.GcmfError("gcm_filters_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _is_torch(a):
+    return hasattr(a, "detach") and hasattr(a, "device")
+
+
+def like(grid_var, field):
+    """grid variable as the same kind of array as `field` (numpy or torch on field's device)."""
+    if _is_torch(field):
+        import torch
+
+        g = grid_var if _is_torch(grid_var) else torch.as_tensor(np.asarray(grid_var))
+        return g.to(device=field.device, dtype=field.dtype)
+    if _is_torch(grid_var):
+        return grid_var.detach().cpu().numpy()
+    return np.asarray(getattr(grid_var, "values", grid_var))
+
+
+# ------------------------------------------------------------------------------------------
+# per-(operator, device, dtype, shape) device state
+# ------------------------------------------------------------------------------------------
+class DevicePlan:
+    """Owns the uploaded coefficient planes and the gcmf_plan handle of one Laplacian on one device."""
+
+    def __init__(self, lap, device_index, np_dtype, ny, nx):
+        torch = _torch()
+        self.lib = _cabi.get_library()
+        self.device = torch.device("cuda", device_index)
+        self.np_dtype = np.dtype(np_dtype)
+        self.ny, self.nx = ny, nx
+        spec = lap._planes
+        self.ncomp = lap.ncomp
+        self.handle = self.lib.plan_create(spec.op, _DT[self.np_dtype], ny, nx, spec.flags, device_index)
+        self.tensors = []  # keep device memory alive
+        self.plane_batch_shapes = []
+        tdt = torch.float32 if self.np_dtype == np.float32 else torch.float64
+        for slot, pl in enumerate(spec.planes):
+            if slot == 0 and spec.op == _cabi.OP_REGULAR5:
+                pl = spec.mask
+                if pl is None:
+                    continue
+                t = torch.as_tensor(np.ascontiguousarray(pl), dtype=torch.uint8).to(self.device)
+            else:
+                if pl is None:
+                    continue
+                t = torch.as_tensor(np.ascontiguousarray(pl)).to(device=self.device, dtype=tdt)
+            if tuple(t.shape[-2:]) != (ny, nx):
+                raise ValueError(f"grid variable plane has shape {tuple(t.shape)}, field has (..., {ny}, {nx})")
+            bshape = tuple(int(s) for s in t.shape[:-2])
+            while bshape and bshape[0] == 1:
+                bshape = bshape[1:]
+            nbp = int(np.prod(bshape)) if bshape else 1
+            t = t.reshape((nbp, ny, nx)).contiguous()
+            self.tensors.append(t)
+            self.plane_batch_shapes.append(bshape)
+            self.lib.plan_set_plane(self.handle, slot, t.data_ptr(), nx, ny * nx, nbp)
+        self._filter_key = None
+
+    def check_batch(self, batch_shape):
+        """Plane batch dims must equal the trailing batch dims of the field (b % plane_nb indexing)."""
+        for bs in self.plane_batch_shapes:
+            if bs and tuple(batch_shape[len(batch_shape) - len(bs):]) != bs:
+                raise ValueError(f"grid variable batch dims {bs} do not match the trailing batch dims of the "
+                                 f"field {tuple(batch_shape)}")
+
+    def set_filter(self, p, c):
+        key = (tuple(float(v) for v in p), float(c))
+        if key != self._filter_key:
+            self.lib.plan_set_filter(self.handle, key[0], key[1])
+            self._filter_key = key
+
+    def __del__(self):
+        try:
+            self.lib.plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_ws_lock = threading.Lock()
+_workspaces = {}
+
+
+def workspace(device, nbytes):
+    """Grow-only scratch per device (uint8 tensor, 512-byte aligned by the caching allocator)."""
+    torch = _torch()
+    with _ws_lock:
+        t = _workspaces.get(device.index)
+        if t is None or t.numel() < nbytes:
+            _workspaces[device.index] = None
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            _workspaces[device.index] = t
+        return t
+
+
+def release_workspaces():
+    with _ws_lock:
+        _workspaces.clear()
+
+
+def device_plan(lap, device_index, np_dtype, ny, nx):
+    key = (device_index, np.dtype(np_dtype).str, ny, nx)
+    st = lap._device_state.get(key)
+    if st is None:
+        st = lap._device_state[key] = DevicePlan(lap, device_index, np_dtype, ny, nx)
+    return st
+
+
+# ------------------------------------------------------------------------------------------
+# array plumbing
+# ------------------------------------------------------------------------------------------
+class _Staged:
+    """Inputs moved to the device as contiguous (nb, ny, nx) tensors + how to hand results back."""
+
+    def __init__(self, lap, fields):
+        torch = _torch()
+        if len(fields) != lap.ncomp:
+            raise ValueError(f"expected {lap.ncomp} field component(s), got {len(fields)}")
+        f0 = fields[0]
+        self.kind = "torch" if _is_torch(f0) else "numpy"
+        if self.kind == "numpy":
+            fields = [np.asarray(getattr(f, "values", f)) for f in fields]
+            f0 = fields[0]
+        shape = tuple(f0.shape)
+        if len(shape) < 2:
+            raise ValueError("fields need at least two dimensions (y, x)")
+        for f in fields[1:]:
+            if tuple(f.shape) != shape:
+                raise ValueError("vector components must have the same shape")
+        self.shape = shape
+        self.ny, self.nx = shape[-2], shape[-1]
+        self.batch_shape = shape[:-2]
+        self.nb = int(np.prod(self.batch_shape)) if self.batch_shape else 1
+        if self.kind == "torch":
+            in_dtype = np.dtype(str(f0.dtype).replace("torch.", ""))
+            self.src_device = f0.device
+            self.device = f0.device if f0.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+            self.pinned = f0.device.type == "cpu" and f0.is_pinned()
+        else:
+            in_dtype = f0.dtype
+            self.src_device = None
+            self.device = torch.device("cuda", torch.cuda.current_device())
+            self.pinned = False
+        if in_dtype.kind != "f" or in_dtype.itemsize not in (4, 8):
+            in_dtype = np.dtype(np.float64)
+        self.np_dtype = lap.compute_dtype(in_dtype)
+        tdt = torch.float32 if self.np_dtype == np.float32 else torch.float64
+        self.tdt = tdt
+        dev = []
+        for f in fields:
+            t = f if self.kind == "torch" else torch.from_numpy(np.ascontiguousarray(f))
+            t = t.to(device=self.device, dtype=tdt, non_blocking=True)
+            dev.append(t.reshape((self.nb, self.ny, self.nx)).contiguous())
+        self.dev = dev
+
+    def out_like(self):
+        torch = _torch()
+        return [torch.empty((self.nb, self.ny, self.nx), dtype=self.tdt, device=self.device) for _ in self.dev]
+
+    def deliver(self, outs, out=None):
+        """Hand results back as the caller's kind of array; `out` (tuple of preallocated numpy arrays
+        or torch CPU/CUDA tensors, one per component) receives them in place when given."""
+        torch = _torch()
+        res = []
+        if out is not None:
+            out = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+            for o, dst in zip(outs, out):
+                t = dst if _is_torch(dst) else torch.from_numpy(dst)
+                t.copy_(o.reshape(self.shape), non_blocking=True)
+                res.append(dst)
+            torch.cuda.current_stream(self.device).synchronize()
+            return tuple(res)
+        for o in outs:
+            o = o.reshape(self.shape)
+            if self.kind == "numpy":
+                res.append(o.cpu().numpy())
+            elif self.src_device.type == "cpu":
+                if self.pinned:
+                    h = torch.empty(o.shape, dtype=o.dtype, pin_memory=True)
+                    h.copy_(o, non_blocking=True)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    res.append(h)
+                else:
+                    res.append(o.cpu())
+            else:
+                res.append(o)
+        return tuple(res)
+
+
+def _specs(tensors):
+    return [(t.data_ptr(), t.shape[-1], t.shape[-2] * t.shape[-1]) for t in tensors]
+
+
+def run_laplacian(lap, fields):
+    """out = Laplacian(fields) on the GPU (one reference ``__call__``)."""
+    torch = _torch()
+    st = _Staged(lap, fields)
+    plan = device_plan(lap, st.device.index, st.np_dtype, st.ny, st.nx)
+    plan.check_batch(st.batch_shape)
+    outs = st.out_like()
+    with torch.cuda.device(st.device):
+        stream = torch.cuda.current_stream(st.device).cuda_stream
+        plan.lib.laplacian(plan.handle, st.nb, _specs(st.dev), _specs(outs), stream)
+    return st.deliver(outs)
+
+
+def run_filter(lap, p, c, fields, out=None):
+    """filtered = filter_func(fields) on the GPU: prepare, n_steps Chebyshev steps, finalize."""
+    torch = _torch()
+    st = _Staged(lap, fields)
+    plan = device_plan(lap, st.device.index, st.np_dtype, st.ny, st.nx)
+    plan.check_batch(st.batch_shape)
+    plan.set_filter(p, c)
+    outs = st.out_like()
+    nbytes = plan.lib.workspace_bytes(plan.handle, st.nb)
+    ws = workspace(st.device, nbytes)
+    with torch.cuda.device(st.device):
+        stream = torch.cuda.current_stream(st.device).cuda_stream
+        plan.lib.filter(plan.handle, st.nb, _specs(st.dev), _specs(outs), ws.data_ptr(), ws.numel(), stream)
+    return st.deliver(outs, out)
+
+
+def filter_device(lap, p, c, dev_in, dev_out):
+    """Device-resident entry used by the scheduler and the benchmark: (nb, ny, nx) CUDA tensors in,
+    preallocated CUDA tensors out, nothing but kernel launches on the current stream."""
+    torch = _torch()
+    t0 = dev_in[0]
+    nb, ny, nx = (int(s) for s in t0.shape)
+    np_dtype = np.dtype(np.float32 if t0.dtype == torch.float32 else np.float64)
+    plan = device_plan(lap, t0.device.index, np_dtype, ny, nx)
+    plan.set_filter(p, c)
+    nbytes = plan.lib.workspace_bytes(plan.handle, nb)
+    ws = workspace(t0.device, nbytes)
+    stream = torch.cuda.current_stream(t0.device).cuda_stream
+    plan.lib.filter(plan.handle, nb, _specs(dev_in), _specs(dev_out), ws.data_ptr(), ws.numel(), stream)
+    return dev_out

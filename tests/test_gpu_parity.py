@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path of gcm_filters_b200 (through the C ABI of libgcmf.so) against the
+CPU oracle and the reference's golden arrays.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from gcm_filters_b200 import Filter, FilterShape, GridType, _cabi
+from gcm_filters_b200.kernels import ALL_KERNELS
+from oracle import fixtures, np_oracle
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+ALL_GRIDS = fixtures.SCALAR_GRIDS + fixtures.VECTOR_GRIDS
+GOLDEN_GRIDS = fixtures.GOLDEN_SCALAR_GRIDS + fixtures.VECTOR_GRIDS
+BIT_EXACT = {"REGULAR", "REGULAR_AREA_WEIGHTED", "REGULAR_WITH_LAND", "REGULAR_WITH_LAND_AREA_WEIGHTED",
+             "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED", "VECTOR_B_GRID"}
+TOL64, TOL32 = 1e-12, 1e-5  # north_star: rel-L2 <= 1e-12 (fp64) / 1e-5 (fp32)
+
+
+def tup(x):
+    return x if isinstance(x, tuple) else (x,)
+
+
+def vec_args(g, gv, fa):
+    fa = dict(fa)
+    if g in fixtures.VECTOR_GRIDS:
+        kx, ky = ("dxT", "dyT") if g == "VECTOR_C_GRID" else ("DXU", "DYU")
+        dxm = float(min(gv[kx].min(), gv[ky].min()))
+        fa["dx_min"] = dxm
+        fa["filter_scale"] = fa["filter_scale"] * dxm
+    return fa
+
+
+def make_filter(g, gv, **fa):
+    fa = dict(fa)
+    if isinstance(fa.get("filter_shape"), str):
+        fa["filter_shape"] = FilterShape[fa["filter_shape"]]
+    return Filter(grid_type=GridType[g], grid_vars=gv, **fa)
+
+
+def run_filter(flt, fields):
+    if len(fields) == 2:
+        return tuple(flt.apply_to_vector(fields[0], fields[1], dims=["y", "x"]))
+    return (flt.apply(fields[0], dims=["y", "x"]),)
+
+
+def test_extension_is_the_cuda_build():
+    lib = _cabi.get_library()
+    assert lib.lib.gcmf_sm_arch() == 100
+
+
+@pytest.mark.parametrize("shape", [(37, 54), (128, 256)])
+@pytest.mark.parametrize("g", ALL_GRIDS)
+def test_laplacian_vs_oracle(g, shape):
+    fields, gv = fixtures.fixture(g, shape)
+    lap = ALL_KERNELS[GridType[g]](**gv)
+    ref = tup(np_oracle.laplacian(g, gv, *fields))
+    got = tup(lap(*fields))
+    for a, b in zip(got, ref):
+        assert isinstance(a, np.ndarray) and a.dtype == np.float64
+        if g in BIT_EXACT:
+            assert np.array_equal(a, b)
+        else:
+            assert rel_l2(a, b) < 1e-14
+
+
+@pytest.mark.parametrize("g", GOLDEN_GRIDS)
+def test_reference_kernel_goldens(g, reference_goldens):
+    # reference tests/test_kernels_validation.py:68-75 (f4 cast, rtol 1e-7)
+    fields, gv = fixtures.fixture(g)
+    got = np.stack(tup(ALL_KERNELS[GridType[g]](**gv)(*fields))).astype("f4")
+    if got.shape[0] == 1:
+        got = got[0]
+    np.testing.assert_allclose(reference_goldens[f"kernels/{g}"], got, rtol=1e-7)
+
+
+@pytest.mark.parametrize("g", GOLDEN_GRIDS)
+def test_reference_filter_goldens(g, reference_goldens):
+    # reference tests/test_filter_validation.py:75-93: Gaussian, filter_scale 8, dx_min 1, n_steps 0
+    fields, gv = fixtures.fixture(g)
+    flt = make_filter(g, gv, filter_scale=8.0, dx_min=1.0, n_steps=0, filter_shape="GAUSSIAN")
+    got = np.stack(run_filter(flt, fields)).astype("f4")
+    if got.shape[0] == 1:
+        got = got[0]
+    np.testing.assert_allclose(reference_goldens[f"filter/{g}"], got, rtol=1e-7)
+
+
+@pytest.mark.parametrize("tag,shape", [("mid", (64, 96)), ("odd", (37, 54))])
+@pytest.mark.parametrize("g", ALL_GRIDS)
+def test_filter_vs_captured_reference(g, tag, shape, ref_outputs):
+    """fp64 outputs of the live reference captured by tests/golden/make_golden.py (the only pin for MOM5U/T)."""
+    fields, gv = fixtures.fixture(g, shape)
+    fa = vec_args(g, gv, dict(filter_scale=8.0, dx_min=1.0, n_steps=0, filter_shape="GAUSSIAN"))
+    got = np.stack(run_filter(make_filter(g, gv, **fa), fields))
+    ref = ref_outputs[f"filter/{tag}/gauss8/{g}"]
+    ref = ref if ref.ndim == 3 else ref[None]
+    assert rel_l2(got, ref) < TOL64
+    if g in BIT_EXACT:
+        assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("g", ALL_GRIDS)
+def test_taper_filter_vs_oracle_f64(g):
+    fields, gv = fixtures.fixture(g, (96, 130))
+    fa = vec_args(g, gv, dict(filter_scale=6.0, dx_min=1.0, filter_shape="TAPER"))
+    ref = tup(np_oracle.apply_filter(g, gv, fields, **fa))
+    got = run_filter(make_filter(g, gv, **fa), fields)
+    for a, b in zip(got, ref):
+        assert rel_l2(a, b) < TOL64
+
+
+@pytest.mark.parametrize("g", ALL_GRIDS)
+def test_filter_f32(g):
+    fields, gv = fixtures.fixture(g, (64, 128))
+    fa = vec_args(g, gv, dict(filter_scale=8.0, dx_min=1.0, filter_shape="GAUSSIAN"))
+    ref = tup(np_oracle.apply_filter(g, gv, fields, **fa))  # fp64 truth
+    gv32 = {k: v.astype(np.float32) for k, v in gv.items()}
+    got = run_filter(make_filter(g, gv32, **fa), tuple(f.astype(np.float32) for f in fields))
+    for a, b in zip(got, ref):
+        assert a.dtype == np.float32
+        assert rel_l2(a, b) < TOL32
+
+
+@pytest.mark.parametrize("g", ["REGULAR_WITH_LAND", "IRREGULAR_WITH_LAND", "TRIPOLAR_POP_WITH_LAND",
+                               "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED", "MOM5T"])
+def test_nan_land_batched(g, ref_outputs):
+    """NaN on land in -> NaN on exactly the land cells out; wet values unaffected."""
+    (f,), gv = fixtures.fixture(g, (48, 64))
+    fb = np.stack([f, f[::-1].copy(), f * f])
+    fb[:, gv["wet_mask"] == 0] = np.nan
+    flt = make_filter(g, gv, filter_scale=8.0, dx_min=1.0)
+    got = flt.apply(fb, dims=["y", "x"])
+    ref = ref_outputs[f"filter/nanbatch/gauss8/{g}"]
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert rel_l2(got, ref) < TOL64
+    # land values must not influence wet results
+    fz = np.where(np.isnan(fb), 123.0, fb)
+    got2 = flt.apply(fz, dims=["y", "x"])
+    wet = ~np.isnan(ref)
+    assert np.array_equal(got2[wet], got[wet])
+
+
+def test_batched_planes_and_4d_field():
+    rng = np.random.default_rng(3)
+    shape = (40, 72)
+    mask = (rng.random((3,) + shape) > 0.3).astype(np.float64)
+    f = rng.random((2, 3) + shape)
+    flt = make_filter("REGULAR_WITH_LAND", {"wet_mask": mask}, filter_scale=4.0, dx_min=1.0)
+    ref = np_oracle.apply_filter("REGULAR_WITH_LAND", {"wet_mask": mask}, (f,), filter_scale=4.0, dx_min=1.0)
+    got = flt.apply(f, dims=["y", "x"])
+    assert got.shape == f.shape and np.array_equal(got, ref)
+
+
+def test_torch_inputs_stay_on_device():
+    import torch
+    (f,), gv = fixtures.fixture("IRREGULAR_WITH_LAND", (64, 96))
+    flt = make_filter("IRREGULAR_WITH_LAND", gv, filter_scale=8.0, dx_min=1.0)
+    ref = flt.apply(f, dims=["y", "x"])
+    t = torch.as_tensor(f).cuda()
+    keep = t.clone()
+    out = flt.apply(t, dims=["y", "x"])
+    assert out.is_cuda and torch.equal(t, keep)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    pinned = torch.as_tensor(f).pin_memory()
+    out = flt.apply(pinned, dims=["y", "x"])
+    assert (not out.is_cuda) and out.is_pinned() and np.array_equal(out.numpy(), ref)
+
+
+# ---- properties that hold at any size (run at benchmark-like sizes) ------------------------------
+@pytest.mark.parametrize("g", ["REGULAR_WITH_LAND", "IRREGULAR_WITH_LAND", "TRIPOLAR_POP_WITH_LAND"])
+def test_conservation_linearity_large(g):
+    shape = (600, 900)
+    (f,), gv = fixtures.fixture(g, shape)
+    area = gv.get("area", gv.get("tarea", np.ones(shape)))
+    lap = ALL_KERNELS[GridType[g]](**gv)
+    d = lap(f)
+    # reference tests/test_kernels.py:15-36: sum(area * Lap f) == 0
+    assert abs(np.sum(area * d)) < 1e-12 * shape[0] * shape[1]
+    flt = make_filter(g, gv, filter_scale=12.0, dx_min=1.0)
+    rng = np.random.default_rng(11)
+    h = rng.standard_normal(shape)
+    a, b, ab = flt.apply(f, None), flt.apply(h, None), flt.apply(2.0 * f - 3.0 * h, None)
+    wet = gv["wet_mask"] == 1
+    assert rel_l2(ab[wet], (2.0 * a - 3.0 * b)[wet]) < 1e-12
+    # reference tests/test_filter.py:118-125: integral conserved, variance reduced
+    np.testing.assert_allclose(np.sum((a * area)[wet]), np.sum((f * area)[wet]), rtol=1e-9)
+    assert np.var(a[wet]) < np.var(f[wet])
+
+
+def test_flux_isotropy_index_kat():
+    """reference tests/test_kernels.py:109-183: a delta next to outlier spacings detects a wrong shift sign."""
+    for g, names in (("IRREGULAR_WITH_LAND", ("dxw", "dyw", "dxs", "dys")),
+                     ("TRIPOLAR_POP_WITH_LAND", ("dxe", "dye", "dxn", "dyn"))):
+        (f,), gv = fixtures.fixture(g)
+        ny, nx = f.shape
+        delta = np.zeros_like(f)
+        delta[99, 225] = 1.0
+        for k in names + (("area",) if g == "IRREGULAR_WITH_LAND" else ("tarea",)):
+            gv[k] = np.ones_like(f)
+        rng = np.random.default_rng(1)
+        for k in names:
+            gv[k] = gv[k].copy()
+            gv[k][rng.integers(0, ny, 40), rng.integers(0, nx, 40)] = 7.0
+        got = ALL_KERNELS[GridType[g]](**gv)(delta)
+        ref = np_oracle.laplacian(g, gv, delta)
+        assert rel_l2(got, ref) < 1e-14
+
+
+def test_tripolar_exchange_kat():
+    # reference tests/test_kernels.py:224-245
+    for g in ("TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED", "TRIPOLAR_POP_WITH_LAND"):
+        f, gv = fixtures.tripolar_unit_fixture(g)
+        nx = f.shape[1]
+        delta = np.zeros_like(f)
+        delta[-1, 10] = 1
+        d = ALL_KERNELS[GridType[g]](**gv)(delta)
+        assert d[-2, 10] == d[-1, nx - 10 - 1]
+
+
+def test_vector_solid_body_rotation():
+    # reference tests/test_kernels.py:251-270: Lap(u = cos(lat), v = 0) == 0
+    for g in fixtures.VECTOR_GRIDS:
+        _, gv = fixtures.fixture(g)
+        _, geolatCu, _, _ = fixtures.spherical_geometry()
+        u = np.cos(geolatCu / 360 * 2 * np.pi)
+        v = np.zeros_like(u)
+        if g == "VECTOR_C_GRID":
+            gv = dict(gv, wet_mask_t=np.ones_like(u), wet_mask_q=np.ones_like(u))
+        du, dv = ALL_KERNELS[GridType[g]](**gv)(u, v)
+        np.testing.assert_allclose(du[1:-1, :], 0.0, atol=1e-12)
+        np.testing.assert_allclose(dv[1:-1, :], 0.0, atol=1e-12)
+
+
+def test_c_abi_error_reporting():
+    lib = _cabi.get_library()
+    with pytest.raises(_cabi.GcmfError, match="unknown op"):
+        lib.plan_create(99, _cabi.GCMF_F64, 8, 8, 0, 0)
+    h = lib.plan_create(_cabi.OP_FLUX, _cabi.GCMF_F64, 8, 8, _cabi.FLAG_WRAP_Y, 0)
+    with pytest.raises(_cabi.GcmfError, match="out of range"):
+        lib.plan_set_plane(h, 7, 1234, 8, 64, 1)
+    import torch
+    x = torch.zeros((1, 8, 8), dtype=torch.float64, device="cuda")
+    y = torch.zeros_like(x)
+    spec = [(x.data_ptr(), 8, 64)]
+    with pytest.raises(_cabi.GcmfError, match="has not been set"):
+        lib.laplacian(h, 1, spec, [(y.data_ptr(), 8, 64)])
+    lib.plan_destroy(h)
