@@ -190,6 +190,7 @@ def gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    engine.set_steps_per_block(args.steps_per_block)
     cfg = build_workload(args.workload, args.nb, rank)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -282,42 +283,70 @@ def gpu_arm(args):
     h2d = sum(h.numel() * h.element_size() for h in host_in)
     d2h = sum(h.numel() * h.element_size() for h in host_out)
 
-    # ---- leg 3: per-launch duration of the dominant kernel (mid-recurrence step) ----------------
+    # ---- leg 3: per-launch durations, same launch sequence as gcmf_filter, CUDA events per launch ----
     plan = engine.device_plan(lap, local, fields[0].dtype, ny, nx)
     plan.set_filter(spec.p, c)
-    ws = engine.workspace(dev, lib.workspace_bytes(plan.handle, nb))
-    bufbytes = lib.workspace_bytes(plan.handle, nb) // (2 * ncomp)
+    wsb = lib.workspace_bytes(plan.handle, nb)
+    ws = engine.workspace(dev, wsb)
+    kfuse = lib.fused_max_steps(plan.handle) if engine.STEPS_PER_BLOCK != 1 else 0
+    nbuf = 4 if kfuse else 2
+    bufbytes = wsb // (nbuf * ncomp)
     spec_of = lambda ts: [(t.data_ptr(), nx, ny * nx) for t in ts]
-    A = [(ws.data_ptr() + k * bufbytes, nx, ny * nx) for k in range(ncomp)]
-    B = [(ws.data_ptr() + (ncomp + k) * bufbytes, nx, ny * nx) for k in range(ncomp)]
+    bufs = [[(ws.data_ptr() + (j * ncomp + k) * bufbytes, nx, ny * nx) for k in range(ncomp)] for j in range(nbuf)]
+    A, B = bufs[0], bufs[1]
     sptr = stream.cuda_stream
-    mid_ms = []
+    records = []
     area = cfg["grid_type"] in ("REGULAR_AREA_WEIGHTED", "REGULAR_WITH_LAND_AREA_WEIGHTED",
                                 "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED")
+
+    def timed(kind, k, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        records.append((kind, k, e0, e1))
+
+    outs = spec_of(dev_out)
     for rep in range(max(1, min(args.steps, 3))):
         X = spec_of(dev_in)
         if area:
             lib.prepare(plan.handle, nb, X, B, sptr)
             X = B
-        lib.cheb_step(plan.handle, nb, 1, X, None, A, spec_of(dev_out), sptr)
+        timed("first", 1, lambda: lib.cheb_step(plan.handle, nb, 1, X, None, A, outs, sptr))
         T1, T2 = A, X
-        for i in range(2, n_steps + 1):
+        i = 2
+        while i <= n_steps:
+            if kfuse and i < n_steps:
+                kk = min(n_steps - i, kfuse)
+                in_ab = T1[0][0] in (A[0][0], B[0][0])
+                O1, O2 = (bufs[2], bufs[3]) if in_ab else (A, B)
+                timed("fused", kk, lambda: lib.cheb_fused(plan.handle, nb, i, kk, T1, T2, O1, O2, outs, sptr))
+                T1, T2 = O1, O2
+                i += kk
+                continue
             D = B if (i == 2 and not area) else T2
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            lib.cheb_step(plan.handle, nb, i, T1, T2, D, spec_of(dev_out), sptr)
-            e1.record(stream)
-            if i < n_steps:
-                mid_ms.append((e0, e1))
+            timed("mid" if i < n_steps else "last", 1,
+                  lambda: lib.cheb_step(plan.handle, nb, i, T1, T2, D, outs, sptr))
             T2, T1 = T1, D
+            i += 1
     torch.cuda.synchronize(dev)
-    mid = float(np.mean([a.elapsed_time(b) for a, b in mid_ms])) if mid_ms else float("nan")
+    per_kind = {}
+    for kind, k, e0, e1 in records:
+        d = per_kind.setdefault((kind, k), [])
+        d.append(e0.elapsed_time(e1))
+    dom = max(per_kind, key=lambda key: sum(per_kind[key]))
+    dom_ms = float(np.mean(per_kind[dom]))
     b_alg = 5 * w * ncomp + c_bytes_per_point(cfg["grid_type"], w) / nb
     peak, peak_src = measured_hbm_peak()
-    achieved = b_alg * nb * ny * nx / (mid * 1e-3) / 1e9
+    # algorithmic bytes of one launch = B_alg per grid-point step x points x steps the launch performs
+    achieved = b_alg * nb * ny * nx * dom[1] / (dom_ms * 1e-3) / 1e9
+    kname = {"fused": f"fused_flux_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)",
+             "mid": "step_kernel<MODE_MID> (one Chebyshev step)", "first": "step_kernel<MODE_FIRST>",
+             "last": "step_kernel<MODE_LAST>"}[dom[0]]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "step_kernel<MODE_MID> (one Chebyshev step)",
-                "ms_per_launch": mid, "algorithmic_bytes_per_pt_step": b_alg, "peak_source": peak_src}
+                "traffic": None, "kernel": kname, "ms_per_launch": dom_ms, "steps_per_launch": dom[1],
+                "algorithmic_bytes_per_pt_step": b_alg, "peak_source": peak_src,
+                "launch_mix_ms": {f"{k[0]}x{k[1]}": [len(v), float(np.mean(v))] for k, v in per_kind.items()}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(prof):
         try:
@@ -389,6 +418,7 @@ def main():
     ap.add_argument("--nb", type=int, default=0, help="override the batch size (levels / time steps)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--steps-per-block", type=int, default=0, help="0 auto, 1 = one-step kernels only")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -18,7 +18,8 @@ FLAG_MASK, FLAG_NAN2NUM, FLAG_FOLD_N, FLAG_CUT_S, FLAG_WRAP_Y, FLAG_AREA = 1, 2,
 EXPORTS = [
     "gcmf_version", "gcmf_sm_arch", "gcmf_last_error", "gcmf_plan_create", "gcmf_plan_destroy",
     "gcmf_plan_set_plane", "gcmf_plan_set_filter", "gcmf_workspace_bytes", "gcmf_laplacian", "gcmf_filter",
-    "gcmf_cheb_step", "gcmf_prepare", "gcmf_launch_count",
+    "gcmf_cheb_step", "gcmf_prepare", "gcmf_launch_count", "gcmf_fused_max_steps", "gcmf_plan_set_steps_per_block",
+    "gcmf_cheb_fused",
 ]
 
 
@@ -61,6 +62,12 @@ class Library:
         lib.gcmf_prepare.argtypes = [vp, i64, fp, fp, vp]
         lib.gcmf_filter.argtypes = [vp, i64, fp, fp, vp, ctypes.c_size_t, vp]
         lib.gcmf_cheb_step.argtypes = [vp, i64, i32, fp, fp, fp, fp, vp]
+        lib.gcmf_fused_max_steps.argtypes = [vp]
+        lib.gcmf_fused_max_steps.restype = ctypes.c_int
+        lib.gcmf_plan_set_steps_per_block.argtypes = [vp, i32]
+        lib.gcmf_plan_set_steps_per_block.restype = ctypes.c_int
+        lib.gcmf_cheb_fused.argtypes = [vp, i64, i32, i32, fp, fp, fp, fp, fp, vp]
+        lib.gcmf_cheb_fused.restype = ctypes.c_int
         for name in ("gcmf_plan_create", "gcmf_plan_destroy", "gcmf_plan_set_plane", "gcmf_plan_set_filter",
                      "gcmf_workspace_bytes", "gcmf_laplacian", "gcmf_prepare", "gcmf_filter", "gcmf_cheb_step"):
             getattr(lib, name).restype = ctypes.c_int
@@ -115,6 +122,16 @@ class Library:
     def cheb_step(self, h, nb, step, t1, t2, t0, bar, stream=0):
         self.check(self.lib.gcmf_cheb_step(h, nb, step, self.fields(t1), self.fields(t2), self.fields(t0),
                                            self.fields(bar), ctypes.c_void_p(stream)))
+
+    def fused_max_steps(self, h):
+        return int(self.lib.gcmf_fused_max_steps(h))
+
+    def set_steps_per_block(self, h, k):
+        self.check(self.lib.gcmf_plan_set_steps_per_block(h, k))
+
+    def cheb_fused(self, h, nb, step, k, t1, t2, t1o, t2o, bar, stream=0):
+        self.check(self.lib.gcmf_cheb_fused(h, nb, step, k, self.fields(t1), self.fields(t2), self.fields(t1o),
+                                            self.fields(t2o), self.fields(bar), ctypes.c_void_p(stream)))
 
     def launch_count(self):
         return int(self.lib.gcmf_launch_count())

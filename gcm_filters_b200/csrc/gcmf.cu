@@ -23,6 +23,7 @@
 #include "../../include/gcmf.h"
 #include "gcmf_internal.h"
 #include "gcmf_stencils.cuh"
+#include "gcmf_fused.cuh"
 
 using namespace gcmf;
 
@@ -98,6 +99,7 @@ extern "C" int gcmf_plan_create(const gcmf_plan_desc* d, gcmf_plan** out) {
     memset(p->plane, 0, sizeof p->plane);
     p->n_steps = 0;
     p->c = 0.0;
+    p->steps_per_block = 0;
 #ifdef GCMF_HOSTEMU
     p->sm_count = 1;
 #else
@@ -153,9 +155,20 @@ static size_t buffer_bytes(const gcmf_plan* p, int64_t nb) {
     return round_up((size_t)nb * p->desc.ny * p->desc.nx * w, 256);
 }
 
+static bool fused_eligible(const gcmf_plan* p);
+static bool plan_uses_fused(const gcmf_plan* p) { return p->steps_per_block != 1 && fused_eligible(p); }
+
+extern "C" int gcmf_plan_set_steps_per_block(gcmf_plan* p, int32_t k) {
+    if (!p) return gcmf_set_error(GCMF_EINVAL, "null plan");
+    if (k < 0 || k > FusedGeom<double>::H)
+        return gcmf_set_error(GCMF_EINVAL, "steps_per_block must be 0 (auto) or 1..%d", FusedGeom<double>::H);
+    p->steps_per_block = k;
+    return GCMF_OK;
+}
+
 extern "C" int gcmf_workspace_bytes(const gcmf_plan* p, int64_t nb, size_t* bytes) {
     if (!p || !bytes || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
-    *bytes = 2 * (size_t)p->ncomp * buffer_bytes(p, nb);
+    *bytes = (size_t)(plan_uses_fused(p) ? 4 : 2) * p->ncomp * buffer_bytes(p, nb);
     return GCMF_OK;
 }
 
@@ -167,14 +180,15 @@ constexpr int BX = 32, BY = 8;
 // from HBM once and hit in L2 for the other nb-1 slices.
 #ifndef GCMF_HOSTEMU
 template <typename T, int VX, class OP, int MODE>
-__global__ void __launch_bounds__(BX* BY) step_kernel(const __grid_constant__ StepParams<T> P, int nxb) {
-    int64_t bid = blockIdx.x;
-    const int xb = (int)(bid % nxb);
+__global__ void __launch_bounds__(BX* BY) step_kernel(const __grid_constant__ StepParams<T> P, unsigned nxb) {
+    unsigned bid = blockIdx.x;  // 32-bit decode: the grid has < 2^31 blocks
+    const unsigned xb = bid % nxb;
     bid /= nxb;
-    const int b = (int)(bid % P.nb);
-    const int yb = (int)(bid / P.nb);
-    const int i0 = (xb * BX + threadIdx.x) * VX;
-    const int j = yb * BY + threadIdx.y;
+    const unsigned nbu = (unsigned)P.nb;
+    const int b = (int)(bid % nbu);
+    const int yb = (int)(bid / nbu);
+    const int i0 = (int)(xb * BX + threadIdx.x) * VX;
+    const int j = yb * BY + (int)threadIdx.y;
     if (i0 < P.g.nx && j < P.g.ny) step_body<T, VX, OP, MODE>(P, b, j, i0);
 }
 
@@ -207,7 +221,7 @@ static int launch_step(const StepParams<T>& P, cudaStream_t st) {
     const int nyb = (P.g.ny + BY - 1) / BY;
     const int64_t nblk = (int64_t)nxb * nyb * P.nb;
     if (nblk > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "grid too large (%lld blocks)", (long long)nblk);
-    step_kernel<T, VX, OP, MODE><<<(unsigned)nblk, dim3(BX, BY), 0, st>>>(P, nxb);
+    step_kernel<T, VX, OP, MODE><<<(unsigned)nblk, dim3(BX, BY), 0, st>>>(P, (unsigned)nxb);
     gcmf_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return GCMF_OK;
@@ -394,6 +408,141 @@ extern "C" int gcmf_cheb_step(gcmf_plan* p, int64_t nb, int32_t step, const gcmf
     return run_step(p, nb, mode, t1_in, t2, t0_out, bar, p0, p1, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ temporally blocked steps
+// Which plans can take the fused path: flux-form operator, doubly periodic (no fold, no band ghost
+// rows), shared 2-D coefficient planes, rows that split into 16-byte vectors, grid at least one tile.
+template <typename T> static bool fused_eligible_t(const gcmf_plan* p) {
+    using G = FusedGeom<T>;
+    if (p->desc.op != GCMF_OP_FLUX) return false;
+    if (p->desc.flags != (GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM)) return false;
+    if (p->desc.nx % G::VX || p->desc.nx < G::TW || p->desc.ny < G::TH) return false;
+    for (int s = 0; s < 3; ++s)
+        if (!p->plane[s].p || p->plane[s].nb != 1 || !aligned(p->plane[s].p, p->plane[s].pitch, 0, G::VX, sizeof(T)))
+            return false;
+    return true;
+}
+static bool fused_eligible(const gcmf_plan* p) {
+    return p->desc.dtype == GCMF_F64 ? fused_eligible_t<double>(p) : fused_eligible_t<float>(p);
+}
+
+#ifdef GCMF_HOSTEMU
+template <typename T> static void fused_flux_host(const FusedParams<T>& P, int ncta) {
+    using G = FusedGeom<T>;
+    std::vector<T> smem((size_t)G::NPLANES * G::PLANE);
+    std::vector<FusedThread<T>> st(G::NTHREADS);
+    const int ntiles = P.ncx * P.ncy;
+    for (int cta = 0; cta < ncta; ++cta) {
+        const int tile = cta % ntiles, grp = cta / ntiles;
+        const int64_t l0 = (int64_t)grp * P.levels_per_cta;
+        const int64_t l1 = l0 + P.levels_per_cta < P.nb ? l0 + P.levels_per_cta : P.nb;
+        if (l0 >= l1) continue;
+        for (auto& v : smem) v = T(12345);
+        FusedTile<T> tl(P, tile, smem.data());
+        for (int r = 0; r < G::TH; ++r) { tl.issue_coef_row(r, nullptr); tl.issue_t1_row(r, l0, 0, nullptr); }
+        int it = 0;
+        for (int64_t l = l0; l < l1; ++l, ++it) {
+            const int buf = it & 1;
+            if (l + 1 < l1) for (int r = 0; r < G::TH; ++r) tl.issue_t1_row(r, l + 1, buf ^ 1, nullptr);
+            for (int t = 0; t < G::NTHREADS; ++t) tl.load_regs(t, l, st[t]);
+            T* Pb = tl.tileP(buf);
+            T* Q = tl.tileQ();
+            for (int t = 0; t < G::NTHREADS; ++t) tl.template step<true>(t, 1, Pb, Q, st[t]);
+            for (int s = 2; s <= P.k; ++s)
+                for (int t = 0; t < G::NTHREADS; ++t) {
+                    if (s & 1) tl.template step<false>(t, s, Pb, Q, st[t]);
+                    else tl.template step<false>(t, s, Q, Pb, st[t]);
+                }
+            for (int t = 0; t < G::NTHREADS; ++t) {
+                if (P.k & 1) tl.store(t, l, Q, Pb, st[t]);
+                else tl.store(t, l, Pb, Q, st[t]);
+            }
+        }
+    }
+}
+#endif
+
+template <typename T>
+static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const gcmf_field* t1, const gcmf_field* t2,
+                       const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st) {
+    using G = FusedGeom<T>;
+    const gcmf_field* all[5] = {t1, t2, t1o, t2o, bar};
+    for (const gcmf_field* f : all)
+        if (!aligned(f->ptr, f->pitch, f->bstride, G::VX, sizeof(T)))
+            return gcmf_set_error(GCMF_EINVAL, "fused step: fields must be 16-byte aligned with vector-multiple strides");
+    if (t1o->ptr == t1->ptr || t1o->ptr == t2->ptr || t2o->ptr == t1->ptr || t2o->ptr == t2->ptr)
+        return gcmf_set_error(GCMF_EINVAL, "fused step: outputs must not alias inputs (neighbouring tiles read them)");
+    FusedParams<T> P;
+    memset(&P, 0, sizeof P);
+    P.g.ny = pl->desc.ny;
+    P.g.nx = pl->desc.nx;
+    P.g.flags = pl->desc.flags;
+    for (int s = 0; s < 3; ++s) P.plane[s] = pl->plane[s];
+    P.t1_in = FieldRef<const T>{(const T*)t1->ptr, t1->pitch, t1->bstride};
+    P.t2_in = FieldRef<const T>{(const T*)t2->ptr, t2->pitch, t2->bstride};
+    P.t1_out = FieldRef<T>{(T*)t1o->ptr, t1o->pitch, t1o->bstride};
+    P.t2_out = FieldRef<T>{(T*)t2o->ptr, t2o->pitch, t2o->bstride};
+    P.bar = FieldRef<T>{(T*)bar->ptr, bar->pitch, bar->bstride};
+    P.c = pl->c;
+    for (int s = 0; s < k; ++s) P.p[s] = pl->p[step0 + s];
+    P.k = k;
+    P.ncx = (pl->desc.nx + G::CW - 1) / G::CW;
+    P.ncy = (pl->desc.ny + G::CH - 1) / G::CH;
+    P.nb = nb;
+    // level slabs: one CTA keeps its coefficient tiles for a whole slab; aim for >= 8 waves of CTAs
+    const int64_t ntiles = (int64_t)P.ncx * P.ncy;
+    int64_t groups = (8LL * pl->sm_count + ntiles - 1) / ntiles;
+    if (groups < 1) groups = 1;
+    if (groups > nb) groups = nb;
+    P.levels_per_cta = (int32_t)((nb + groups - 1) / groups);
+    groups = (nb + P.levels_per_cta - 1) / P.levels_per_cta;
+    const int64_t ncta = ntiles * groups;
+    if (ncta > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "fused step: grid too large");
+#ifdef GCMF_HOSTEMU
+    (void)st;
+    fused_flux_host<T>(P, (int)ncta);
+    gcmf_count_launch(1);
+    return GCMF_OK;
+#else
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[sizeof(T) == 8]) {
+        CUDA_TRY(cudaFuncSetAttribute(fused_flux_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)G::SMEM_BYTES));
+        attr_done[sizeof(T) == 8] = true;
+    }
+    fused_flux_kernel<T><<<(unsigned)ncta, G::NTHREADS, G::SMEM_BYTES, st>>>(P);
+    gcmf_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCMF_OK;
+#endif
+}
+
+extern "C" int gcmf_fused_max_steps(const gcmf_plan* p) {
+    if (!p) return 0;
+    return fused_eligible(p) ? FusedGeom<double>::H : 0;
+}
+
+extern "C" int gcmf_cheb_fused(gcmf_plan* p, int64_t nb, int32_t step, int32_t k, const gcmf_field* t1_in,
+                               const gcmf_field* t2_in, const gcmf_field* t1_out, const gcmf_field* t2_out,
+                               const gcmf_field* bar, void* stream) {
+    if (!p || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
+    if (p->n_steps < 2) return gcmf_set_error(GCMF_ESTATE, "gcmf_plan_set_filter has not been called");
+    if (!fused_eligible(p)) return gcmf_set_error(GCMF_EINVAL, "this plan has no fused path (see gcmf_fused_max_steps)");
+    if (k < 1 || k > FusedGeom<double>::H) return gcmf_set_error(GCMF_EINVAL, "k = %d outside 1..%d", k, FusedGeom<double>::H);
+    if (step < 2 || step + k - 1 >= p->n_steps)
+        return gcmf_set_error(GCMF_EINVAL, "fused steps %d..%d must lie strictly inside 2..%d", step, step + k - 1,
+                              p->n_steps - 1);
+    TRY(check_planes(p));
+    TRY(check_fields(p, t1_in, "t1_in"));
+    TRY(check_fields(p, t2_in, "t2_in"));
+    TRY(check_fields(p, t1_out, "t1_out"));
+    TRY(check_fields(p, t2_out, "t2_out"));
+    TRY(check_fields(p, bar, "bar"));
+    CUDA_TRY(cudaSetDevice(p->desc.device));
+    if (p->desc.dtype == GCMF_F64)
+        return run_fused_t<double>(p, nb, step, k, t1_in, t2_in, t1_out, t2_out, bar, (cudaStream_t)stream);
+    return run_fused_t<float>(p, nb, step, k, t1_in, t2_in, t1_out, t2_out, bar, (cudaStream_t)stream);
+}
+
 extern "C" int gcmf_filter(gcmf_plan* p, int64_t nb, const gcmf_field* in, const gcmf_field* out, void* workspace,
                            size_t workspace_bytes, void* stream) {
     if (!p || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
@@ -426,11 +575,29 @@ extern "C" int gcmf_filter(gcmf_plan* p, int64_t nb, const gcmf_field* in, const
     TRY(gcmf_cheb_step(p, nb, 1, X, nullptr, A, out, stream));
     gcmf_field T1[2], T2[2];
     for (int k = 0; k < nc; ++k) { T1[k] = A[k]; T2[k] = X[k]; }
-    for (int i = 2; i <= p->n_steps; ++i) {  // filter.py:196-206; pointer rotation replaces the two .copy()
-        gcmf_field D[2];
-        for (int k = 0; k < nc; ++k) D[k] = (i == 2 && !area) ? B[k] : T2[k];  // never write the user's input
-        TRY(gcmf_cheb_step(p, nb, i, T1, T2, D, out, stream));
-        for (int k = 0; k < nc; ++k) { T2[k] = T1[k]; T1[k] = D[k]; }
+    int i = 2;
+    const int n = p->n_steps;
+    const bool fuse = plan_uses_fused(p);
+    while (i <= n) {  // filter.py:196-206; pointer rotation replaces the two .copy() per step
+        const int kmax = p->steps_per_block ? p->steps_per_block : FusedGeom<double>::H;
+        // fused blocks cover the mid steps 2..n-1 (step 2 reads the prepared input as T2, never writes it)
+        if (fuse && i < n) {
+            const int kk = (n - i) < kmax ? (n - i) : kmax;  // steps i .. i+kk-1 <= n-1
+            // ping-pong between the two workspace pairs: (A,B) <-> (C,D)
+            gcmf_field C{(char*)workspace + (size_t)2 * bb, pitch, bs}, D{(char*)workspace + (size_t)3 * bb, pitch, bs};
+            const bool in_ab = (T1[0].ptr == A[0].ptr || T1[0].ptr == B[0].ptr);
+            gcmf_field O1 = in_ab ? C : A[0], O2 = in_ab ? D : B[0];
+            TRY(gcmf_cheb_fused(p, nb, i, kk, &T1[0], &T2[0], &O1, &O2, out, stream));
+            T1[0] = O1;
+            T2[0] = O2;
+            i += kk;
+            continue;
+        }
+        gcmf_field Dst[2];
+        for (int k = 0; k < nc; ++k) Dst[k] = (i == 2 && !area) ? B[k] : T2[k];  // never write the user's input
+        TRY(gcmf_cheb_step(p, nb, i, T1, T2, Dst, out, stream));
+        for (int k = 0; k < nc; ++k) { T2[k] = T1[k]; T1[k] = Dst[k]; }
+        ++i;
     }
     return GCMF_OK;
 }

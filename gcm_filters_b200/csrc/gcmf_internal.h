@@ -16,6 +16,7 @@ struct gcmf_plan {
     std::vector<double> p;  // Chebyshev coefficients p[0..n_steps]
     double c;
     int sm_count;
+    int steps_per_block;  // 0 = auto (fuse when eligible), 1 = never fuse, 2..4 = cap
 };
 
 int gcmf_set_error(int code, const char* fmt, ...);

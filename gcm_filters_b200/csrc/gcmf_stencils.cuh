@@ -27,11 +27,31 @@ template <typename T> struct Lim;
 template <> struct Lim<float> { static GCMF_HD float big() { return 3.402823466e+38f; } };
 template <> struct Lim<double> { static GCMF_HD double big() { return 1.7976931348623157e+308; } };
 
-// numpy.nan_to_num: NaN -> 0, +-inf -> +-largest finite value
-template <typename T> GCMF_HD T nan2num(T x) {
-    if (x != x) return T(0);
-    const T m = Lim<T>::big();
-    return x > m ? m : (x < -m ? -m : x);
+// numpy.nan_to_num: NaN -> 0, +-inf -> +-largest finite value.  Finite values (the hot case) cost
+// one exponent test; NaN / inf take the rare branch.
+GCMF_HD double nan2num(double x) {
+#ifdef __CUDA_ARCH__
+    const unsigned hi = (unsigned)__double2hiint(x);
+    if ((hi & 0x7ff00000u) == 0x7ff00000u) {
+#else
+    if (!(x - x == 0.0)) {
+#endif
+        if (x != x) return 0.0;
+        return x > 0.0 ? Lim<double>::big() : -Lim<double>::big();
+    }
+    return x;
+}
+GCMF_HD float nan2num(float x) {
+#ifdef __CUDA_ARCH__
+    const unsigned u = __float_as_uint(x);
+    if ((u & 0x7f800000u) == 0x7f800000u) {
+#else
+    if (!(x - x == 0.0f)) {
+#endif
+        if (x != x) return 0.0f;
+        return x > 0.0f ? Lim<float>::big() : -Lim<float>::big();
+    }
+    return x;
 }
 
 struct PlaneRef {
@@ -162,7 +182,7 @@ GCMF_HD void load_nb(Nb<S, VX>& o, const S* base, int64_t pitch, const Pt& q, in
 }
 
 template <typename S> GCMF_HD const S* plane_base(const PlaneRef& pl, int b) {
-    return reinterpret_cast<const S*>(pl.p) + (int64_t)(pl.nb > 1 ? b % pl.nb : 0) * pl.bstride;
+    return reinterpret_cast<const S*>(pl.p) + (int64_t)(pl.nb > 1 ? (int)((unsigned)b % (unsigned)pl.nb) : 0) * pl.bstride;
 }
 
 // =====================================================================================

@@ -11,6 +11,17 @@ from . import _cabi
 
 _DT = {np.dtype(np.float32): _cabi.GCMF_F32, np.dtype(np.float64): _cabi.GCMF_F64}
 
+# Temporal blocking of the Chebyshev steps: 0 = auto (fuse up to 4 steps per HBM round trip whenever the
+# operator/grid has a fused kernel), 1 = never fuse, 2..4 = cap.  Results are bit-identical either way.
+STEPS_PER_BLOCK = 0
+
+
+def set_steps_per_block(k):
+    global STEPS_PER_BLOCK
+    if k not in (0, 1, 2, 3, 4):
+        raise ValueError("steps_per_block must be 0 (auto) or 1..4")
+    STEPS_PER_BLOCK = int(k)
+
 
 def _torch():
     import torch
@@ -75,6 +86,7 @@ class DevicePlan:
             self.plane_batch_shapes.append(bshape)
             self.lib.plan_set_plane(self.handle, slot, t.data_ptr(), nx, ny * nx, nbp)
         self._filter_key = None
+        self._spb = 0
 
     def check_batch(self, batch_shape):
         """Plane batch dims must equal the trailing batch dims of the field (b % plane_nb indexing)."""
@@ -84,6 +96,9 @@ class DevicePlan:
                                  f"field {tuple(batch_shape)}")
 
     def set_filter(self, p, c):
+        if self._spb != STEPS_PER_BLOCK:
+            self.lib.set_steps_per_block(self.handle, STEPS_PER_BLOCK)
+            self._spb = STEPS_PER_BLOCK
         key = (tuple(float(v) for v in p), float(c))
         if key != self._filter_key:
             self.lib.plan_set_filter(self.handle, key[0], key[1])

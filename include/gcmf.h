@@ -143,6 +143,20 @@ int gcmf_filter(gcmf_plan *plan, int64_t nb, const gcmf_field *in, const gcmf_fi
 int gcmf_cheb_step(gcmf_plan *plan, int64_t nb, int32_t step, const gcmf_field *t1_in, const gcmf_field *t2,
                    const gcmf_field *t0_out, const gcmf_field *bar, void *stream);
 
+/* Temporal blocking (north_star item 2; no counterpart in the reference, which makes ~26 array passes
+ * per step).  gcmf_fused_max_steps: how many recurrence steps this plan can fuse into one HBM round
+ * trip (0 = no fused path for this operator / grid; the one-step kernels are used).
+ * gcmf_plan_set_steps_per_block: 0 = auto (default), 1 = never fuse, 2..4 = cap the block length.
+ * gcmf_cheb_fused: steps step .. step+k-1 (all strictly between 1 and n_steps) in one launch:
+ *   reads T_{step-1} (`t1_in`) and T_{step-2} (`t2_in`), writes T_{step+k-1} (`t1_out`) and
+ *   T_{step+k-2} (`t2_out`), and adds sum_s p[s] T_s to `bar`.  Scalar operators only; outputs must
+ *   not alias inputs (neighbouring tiles read the inputs' halos). */
+int gcmf_fused_max_steps(const gcmf_plan *plan);
+int gcmf_plan_set_steps_per_block(gcmf_plan *plan, int32_t k);
+int gcmf_cheb_fused(gcmf_plan *plan, int64_t nb, int32_t step, int32_t k, const gcmf_field *t1_in,
+                    const gcmf_field *t2_in, const gcmf_field *t1_out, const gcmf_field *t2_out,
+                    const gcmf_field *bar, void *stream);
+
 /* x = field * area (AreaWeightedMixin.prepare, kernels.py:100-101); a copy when the plan has no
  * GCMF_FLAG_AREA.  gcmf_filter calls this itself. */
 int gcmf_prepare(gcmf_plan *plan, int64_t nb, const gcmf_field *in, const gcmf_field *out, void *stream);

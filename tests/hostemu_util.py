@@ -72,3 +72,7 @@ class EmuPlan:
         for a, b in zip(fin, keep):
             assert np.array_equal(a, b, equal_nan=True), "input was modified"
         return [o.reshape(np.shape(fields[0])) for o in out]
+
+
+def emu_set_steps_per_block(plan, k):
+    plan.lib.set_steps_per_block(plan.h, k)

@@ -1,0 +1,80 @@
+"""CPU checks of the temporally blocked kernel (gcmf_fused.cuh) through the host emulator: the
+fused path must be bit-identical to the one-step path, and within tolerance of the oracle."""
+import numpy as np
+import pytest
+
+from gcm_filters_b200 import FilterShape, GridType
+from gcm_filters_b200.filter import _compute_filter_spec, _shift_scale
+from gcm_filters_b200.kernels import ALL_KERNELS
+from oracle import fixtures, np_oracle
+
+from conftest import rel_l2
+from hostemu_util import EmuPlan, emu_set_steps_per_block
+
+
+def _case(g, shape, nb, dtype, n_steps, seed=0):
+    (f,), gv = fixtures.fixture(g, shape)
+    rng = np.random.default_rng(seed)
+    fb = np.stack([f * (1 + 0.1 * k) + 0.05 * rng.standard_normal(shape) for k in range(nb)])
+    fb[:, gv["wet_mask"] == 0] = np.nan
+    lap = ALL_KERNELS[GridType[g]](**gv)
+    spec = _compute_filter_spec(8.0, 1.0, FilterShape.GAUSSIAN, np.pi, 2, n_steps)
+    return fb.astype(dtype), gv, lap, spec
+
+
+@pytest.mark.parametrize("g", ["IRREGULAR_WITH_LAND", "MOM5T"])
+@pytest.mark.parametrize("shape,nb,n_steps", [((70, 250), 3, 11), ((36, 128), 1, 7), ((100, 136), 2, 4)])
+def test_fused_equals_unfused_f64(g, shape, nb, n_steps):
+    fb, gv, lap, spec = _case(g, shape, nb, np.float64, n_steps)
+    c = _shift_scale(spec, lap)
+    fused = EmuPlan(lap, np.float64, *shape)
+    assert fused.lib.fused_max_steps(fused.h) == 4
+    n0 = fused.lib.launch_count()
+    (a,) = fused.filter((fb,), spec.p, c)
+    launches = fused.lib.launch_count() - n0
+    assert launches == 2 + -(-(n_steps - 2) // 4)  # first + last + ceil(mid/4) fused blocks
+    plain = EmuPlan(lap, np.float64, *shape)
+    emu_set_steps_per_block(plain, 1)
+    (b,) = plain.filter((fb,), spec.p, c)
+    assert np.array_equal(a, b, equal_nan=True)
+    ref = np_oracle.run_recurrence(np_oracle.make_operator(g, gv), np_oracle.FilterSpec(*spec), (fb,))
+    assert rel_l2(a, ref) < 1e-12
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_fused_block_cap(k):
+    fb, gv, lap, spec = _case("IRREGULAR_WITH_LAND", (64, 200), 2, np.float64, 9)
+    c = _shift_scale(spec, lap)
+    capped = EmuPlan(lap, np.float64, 64, 200)
+    emu_set_steps_per_block(capped, k)
+    (a,) = capped.filter((fb,), spec.p, c)
+    plain = EmuPlan(lap, np.float64, 64, 200)
+    emu_set_steps_per_block(plain, 1)
+    (b,) = plain.filter((fb,), spec.p, c)
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_fused_f32():
+    shape = (60, 300)
+    fb, gv, lap, spec = _case("IRREGULAR_WITH_LAND", shape, 2, np.float32, 10)
+    c = _shift_scale(spec, lap)
+    fused = EmuPlan(lap, np.float32, *shape)
+    assert fused.lib.fused_max_steps(fused.h) == 4
+    (a,) = fused.filter((fb,), spec.p, c)
+    plain = EmuPlan(lap, np.float32, *shape)
+    emu_set_steps_per_block(plain, 1)
+    (b,) = plain.filter((fb,), spec.p, c)
+    assert np.array_equal(a, b, equal_nan=True)
+    ref = np_oracle.run_recurrence(np_oracle.make_operator("IRREGULAR_WITH_LAND", gv), np_oracle.FilterSpec(*spec),
+                                   (fb.astype(np.float64),))
+    assert rel_l2(a, ref) < 1e-5
+
+
+def test_fused_not_offered_for_folded_or_small_grids():
+    (f,), gv = fixtures.fixture("TRIPOLAR_POP_WITH_LAND", (64, 200))
+    lap = ALL_KERNELS[GridType.TRIPOLAR_POP_WITH_LAND](**gv)
+    assert EmuPlan(lap, np.float64, 64, 200).lib.fused_max_steps(EmuPlan(lap, np.float64, 64, 200).h) == 0
+    (f,), gv = fixtures.fixture("IRREGULAR_WITH_LAND", (30, 100))
+    lap = ALL_KERNELS[GridType.IRREGULAR_WITH_LAND](**gv)
+    pl = EmuPlan(lap, np.float64, 30, 100)
+    assert pl.lib.fused_max_steps(pl.h) == 0
