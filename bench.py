@@ -348,10 +348,14 @@ def gpu_arm(args):
                 "algorithmic_bytes_per_pt_step": b_alg, "peak_source": peak_src,
                 "launch_mix_ms": {f"{k[0]}x{k[1]}": [len(v), float(np.mean(v))] for k, v in per_kind.items()}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(prof):
+    if os.path.isfile(prof):  # ncu-measured DRAM bytes per unit of the dominant kernel (committed capture)
         try:
             with open(prof) as fh:
-                roofline["traffic"] = json.load(fh).get(args.workload)
+                tr = json.load(fh)
+            key = args.workload if dom[0] == "fused" else args.workload + "_onestep"
+            if key in tr:
+                roofline["traffic"] = tr[key]["bytes_per_pt_step"] * nb * ny * nx * dom[1]
+                roofline["traffic_source"] = tr[key]["source"]
         except Exception:
             pass
 
