@@ -361,6 +361,7 @@ extern "C" int gcmf_prepare(gcmf_plan* p, int64_t nb, const gcmf_field* in, cons
                                             (int64_t)j * p->plane[1].pitch + i);
                     }
                 }
+    if (p->desc.flags & GCMF_FLAG_AREA) gcmf_count_launch(p->ncomp);
     return GCMF_OK;
 #else
     for (int k = 0; k < p->ncomp; ++k) {
@@ -409,26 +410,38 @@ extern "C" int gcmf_cheb_step(gcmf_plan* p, int64_t nb, int32_t step, const gcmf
 }
 
 // ------------------------------------------------------------------ temporally blocked steps
-// Which plans can take the fused path: flux-form operator, doubly periodic (no fold, no band ghost
-// rows), shared 2-D coefficient planes, rows that split into 16-byte vectors, grid at least one tile.
-template <typename T> static bool fused_eligible_t(const gcmf_plan* p) {
+// Which plans can take the fused path: FLUX or REGULAR5 operator, doubly periodic (no fold, no band
+// ghost rows), shared 2-D planes, rows that split into 16-byte vectors, grid at least one tile.
+// Returns FK_FLUX / FK_REG5 or -1.
+template <typename T> static int fused_kind_t(const gcmf_plan* p) {
     using G = FusedGeom<T>;
-    if (p->desc.op != GCMF_OP_FLUX) return false;
-    if (p->desc.flags != (GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM)) return false;
-    if (p->desc.nx % G::VX || p->desc.nx < G::TW || p->desc.ny < G::TH) return false;
-    for (int s = 0; s < 3; ++s)
-        if (!p->plane[s].p || p->plane[s].nb != 1 || !aligned(p->plane[s].p, p->plane[s].pitch, 0, G::VX, sizeof(T)))
-            return false;
-    return true;
+    const int fl = p->desc.flags;
+    if (p->desc.nx % G::VX || p->desc.nx < G::TW || p->desc.ny < G::TH) return -1;
+    if (p->desc.op == GCMF_OP_FLUX) {
+        if (fl != (GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM)) return -1;
+        for (int s = 0; s < 3; ++s)
+            if (!p->plane[s].p || p->plane[s].nb != 1 ||
+                !aligned(p->plane[s].p, p->plane[s].pitch, 0, G::VX, sizeof(T)))
+                return -1;
+        return FK_FLUX;
+    }
+    if (p->desc.op == GCMF_OP_REGULAR5) {
+        const int core = fl & ~GCMF_FLAG_AREA;  // prepare / finalize happen outside the fused mid steps
+        if (core == GCMF_FLAG_WRAP_Y) return FK_REG5;
+        if (core == (GCMF_FLAG_WRAP_Y | GCMF_FLAG_MASK | GCMF_FLAG_NAN2NUM) && p->plane[0].p && p->plane[0].nb == 1)
+            return FK_REG5;
+    }
+    return -1;
 }
-static bool fused_eligible(const gcmf_plan* p) {
-    return p->desc.dtype == GCMF_F64 ? fused_eligible_t<double>(p) : fused_eligible_t<float>(p);
+static int fused_kind(const gcmf_plan* p) {
+    return p->desc.dtype == GCMF_F64 ? fused_kind_t<double>(p) : fused_kind_t<float>(p);
 }
+static bool fused_eligible(const gcmf_plan* p) { return fused_kind(p) >= 0; }
 
 #ifdef GCMF_HOSTEMU
-template <typename T> static void fused_flux_host(const FusedParams<T>& P, int ncta) {
+template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, int ncta) {
     using G = FusedGeom<T>;
-    std::vector<T> smem((size_t)G::NPLANES * G::PLANE);
+    std::vector<T> smem((size_t)G::ntiles(KIND) * G::PLANE);
     std::vector<FusedThread<T>> st(G::NTHREADS);
     const int ntiles = P.ncx * P.ncy;
     for (int cta = 0; cta < ncta; ++cta) {
@@ -437,27 +450,38 @@ template <typename T> static void fused_flux_host(const FusedParams<T>& P, int n
         const int64_t l1 = l0 + P.levels_per_cta < P.nb ? l0 + P.levels_per_cta : P.nb;
         if (l0 >= l1) continue;
         for (auto& v : smem) v = T(12345);
-        FusedTile<T> tl(P, tile, smem.data());
-        for (int r = 0; r < G::TH; ++r) { tl.issue_coef_row(r, nullptr); tl.issue_t1_row(r, l0, 0, nullptr); }
-        int it = 0;
-        for (int64_t l = l0; l < l1; ++l, ++it) {
-            const int buf = it & 1;
-            if (l + 1 < l1) for (int r = 0; r < G::TH; ++r) tl.issue_t1_row(r, l + 1, buf ^ 1, nullptr);
-            for (int t = 0; t < G::NTHREADS; ++t) tl.load_regs(t, l, st[t]);
-            T* Pb = tl.tileP(buf);
-            T* Q = tl.tileQ();
-            for (int t = 0; t < G::NTHREADS; ++t) tl.template step<true>(t, 1, Pb, Q, st[t]);
-            for (int s = 2; s <= P.k; ++s)
+        FusedTile<T, KIND> tl(P, tile, smem.data());
+        for (int r = 0; r < G::TH; ++r) {
+            if (KIND == FK_FLUX) tl.issue_coef_row(r, nullptr);
+            tl.issue_state_row(r, l0, nullptr);
+        }
+        for (int t = 0; t < G::NTHREADS; ++t) tl.load_mask(t, st[t]);
+        for (int64_t l = l0; l < l1; ++l) {
+            for (int t = 0; t < G::NTHREADS; ++t) tl.load_bar(t, l, st[t]);
+            for (int t = 0; t < G::NTHREADS; ++t) tl.extract(t, st[t]);
+            if (l + 1 < l1) for (int r = 0; r < G::TH; ++r) tl.issue_state_row(r, l + 1, nullptr);
+            for (int s = 1; s <= P.k; ++s)
                 for (int t = 0; t < G::NTHREADS; ++t) {
-                    if (s & 1) tl.template step<false>(t, s, Pb, Q, st[t]);
-                    else tl.template step<false>(t, s, Q, Pb, st[t]);
+                    if (s & 1) tl.step(t, s, tl.tileS(0), tl.tileS(1), st[t]);
+                    else tl.step(t, s, tl.tileS(1), tl.tileS(0), st[t]);
                 }
-            for (int t = 0; t < G::NTHREADS; ++t) {
-                if (P.k & 1) tl.store(t, l, Q, Pb, st[t]);
-                else tl.store(t, l, Pb, Q, st[t]);
-            }
+            for (int t = 0; t < G::NTHREADS; ++t) tl.store(t, l, st[t]);
         }
     }
+}
+#else
+template <typename T, int KIND> static int launch_fused_kernel(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
+    using G = FusedGeom<T>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(fused_kernel<T, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)G::smem_bytes(KIND)));
+        attr_done = true;
+    }
+    fused_kernel<T, KIND><<<(unsigned)ncta, G::NTHREADS, G::smem_bytes(KIND), st>>>(P);
+    gcmf_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCMF_OK;
 }
 #endif
 
@@ -465,6 +489,7 @@ template <typename T>
 static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const gcmf_field* t1, const gcmf_field* t2,
                        const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st) {
     using G = FusedGeom<T>;
+    const int kind = fused_kind_t<T>(pl);
     const gcmf_field* all[5] = {t1, t2, t1o, t2o, bar};
     for (const gcmf_field* f : all)
         if (!aligned(f->ptr, f->pitch, f->bstride, G::VX, sizeof(T)))
@@ -499,20 +524,13 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
     if (ncta > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "fused step: grid too large");
 #ifdef GCMF_HOSTEMU
     (void)st;
-    fused_flux_host<T>(P, (int)ncta);
+    if (kind == FK_FLUX) fused_host<T, FK_FLUX>(P, (int)ncta);
+    else fused_host<T, FK_REG5>(P, (int)ncta);
     gcmf_count_launch(1);
     return GCMF_OK;
 #else
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[sizeof(T) == 8]) {
-        CUDA_TRY(cudaFuncSetAttribute(fused_flux_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)G::SMEM_BYTES));
-        attr_done[sizeof(T) == 8] = true;
-    }
-    fused_flux_kernel<T><<<(unsigned)ncta, G::NTHREADS, G::SMEM_BYTES, st>>>(P);
-    gcmf_count_launch(1);
-    CUDA_TRY(cudaGetLastError());
-    return GCMF_OK;
+    if (kind == FK_FLUX) return launch_fused_kernel<T, FK_FLUX>(P, ncta, st);
+    return launch_fused_kernel<T, FK_REG5>(P, ncta, st);
 #endif
 }
 

@@ -78,3 +78,29 @@ def test_fused_not_offered_for_folded_or_small_grids():
     lap = ALL_KERNELS[GridType.IRREGULAR_WITH_LAND](**gv)
     pl = EmuPlan(lap, np.float64, 30, 100)
     assert pl.lib.fused_max_steps(pl.h) == 0
+
+
+@pytest.mark.parametrize("g", ["REGULAR", "REGULAR_WITH_LAND", "REGULAR_WITH_LAND_AREA_WEIGHTED", "REGULAR_AREA_WEIGHTED"])
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (70, 250)), (np.float32, (40, 300))])
+def test_fused_regular5(g, dtype, shape):
+    (f,), gv = fixtures.fixture(g, shape)
+    fb = np.stack([f, f * f, 1 - f])
+    if "wet_mask" in gv:
+        fb[:, gv["wet_mask"] == 0] = np.nan
+    lap = ALL_KERNELS[GridType[g]](**gv)
+    spec = _compute_filter_spec(8.0, 1.0, FilterShape.GAUSSIAN, np.pi, 2, 11)
+    c = _shift_scale(spec, lap)
+    fused = EmuPlan(lap, dtype, *shape)
+    assert fused.lib.fused_max_steps(fused.h) == 4
+    n0 = fused.lib.launch_count()
+    (a,) = fused.filter((fb.astype(dtype),), spec.p, c)
+    assert fused.lib.launch_count() - n0 == 2 + 3 + (1 if "AREA" in g else 0)
+    plain = EmuPlan(lap, dtype, *shape)
+    emu_set_steps_per_block(plain, 1)
+    (b,) = plain.filter((fb.astype(dtype),), spec.p, c)
+    assert np.array_equal(a, b, equal_nan=True)
+    ref = np_oracle.run_recurrence(np_oracle.make_operator(g, gv), np_oracle.FilterSpec(*spec), (fb,))
+    if dtype == np.float64:
+        assert np.array_equal(a, ref, equal_nan=True)  # REGULAR5 family: bit-identical to the reference arithmetic
+    else:
+        assert rel_l2(a, ref) < 1e-5
