@@ -461,10 +461,7 @@ template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, 
             for (int t = 0; t < G::NTHREADS; ++t) tl.extract(t, st[t]);
             if (l + 1 < l1) for (int r = 0; r < G::TH; ++r) tl.issue_state_row(r, l + 1, nullptr);
             for (int s = 1; s <= P.k; ++s)
-                for (int t = 0; t < G::NTHREADS; ++t) {
-                    if (s & 1) tl.step(t, s, tl.tileS(0), tl.tileS(1), st[t]);
-                    else tl.step(t, s, tl.tileS(1), tl.tileS(0), st[t]);
-                }
+                for (int t = 0; t < G::NTHREADS; ++t) tl.step(t, s, st[t]);
             for (int t = 0; t < G::NTHREADS; ++t) tl.store(t, l, st[t]);
         }
     }

@@ -245,68 +245,74 @@ template <typename T, int KIND> struct FusedTile {
         }
     }
 
-    // phase: recurrence step s (1-based) on the region [s, TH-s) x [s, TW-s); S = source work tile, D = destination
-    GCMF_HD void step(int tid, int s, const T* __restrict__ S, T* __restrict__ D, FusedThread<T>& st) const {
+    // phase: recurrence step s (1-based) on the region [s, TH-s) x [s, TW-s); S = source work tile, D = destination.
+    // X1 holds T_{i-1} (raw), X2 holds T_{i-2}; the new T_i is written over X2, so consecutive steps just swap
+    // the roles of the two register arrays (no moves).  ALLROWS: the thread's R rows all lie in the region for
+    // every s <= H (threads with 0 < ty < NTY-1), which removes every branch from the row loop.
+    template <bool ALLROWS>
+    GCMF_HD void step_rows(int tid, int s, const T* __restrict__ S, T* __restrict__ D, T (&X1)[G::R][G::VX],
+                           T (&X2)[G::R][G::VX], FusedThread<T>& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
-        if (lc0 + G::VX <= s || lc0 >= G::TW - s) return;  // column group outside the region
         const int lr0 = ty * G::R;
-        const int iw = lc0 > 0 ? lc0 - 1 : 0;
-        const int ie = lc0 + G::VX < G::TW ? lc0 + G::VX : G::TW - 1;
+        const int off0 = lr0 * G::TW + lc0;
+        const T* Sc = S + off0;
+        const T* Sw = Sc - (lc0 > 0 ? 1 : 0);                          // west neighbour of column lc0 (clamped)
+        const T* Se = Sc + (lc0 + G::VX < G::TW ? G::VX : G::VX - 1);  // east neighbour of column lc0+VX-1 (clamped)
         const T c = (T)P.c;
         const double pk = P.p[s - 1];
         T o[G::R][G::VX], os[G::VX], on[G::VX];
 #pragma unroll
         for (int q = 0; q < G::R; ++q)
 #pragma unroll
-            for (int v = 0; v < G::VX; ++v) o[q][v] = sanitize(st.t1[q][v], (st.mbits >> (q * G::VX + v)) & 1u);
-        if (lr0 > 0) Ld<T, G::VX>::go(S + (lr0 - 1) * G::TW + lc0, os);
-        if (lr0 + G::R < G::TH) Ld<T, G::VX>::go(S + (lr0 + G::R) * G::TW + lc0, on);
+            for (int v = 0; v < G::VX; ++v) o[q][v] = sanitize(X1[q][v], (st.mbits >> (q * G::VX + v)) & 1u);
+        if (ALLROWS || lr0 > 0) Ld<T, G::VX>::go(Sc - G::TW, os);
+        if (ALLROWS || lr0 + G::R < G::TH) Ld<T, G::VX>::go(Sc + G::R * G::TW, on);
         T cn_prev[G::VX];
         bool have_prev = false;
 #pragma unroll
         for (int q = 0; q < G::R; ++q) {
             const int lr = lr0 + q;
-            if (lr < s || lr >= G::TH - s) {
+            if (!ALLROWS && (lr < s || lr >= G::TH - s)) {
                 have_prev = false;
                 continue;
             }
-            const T ow = S[lr * G::TW + iw];
-            const T oe = S[lr * G::TW + ie];
+            const T ow = Sw[q * G::TW];
+            const T oe = Se[q * G::TW];
             T t0[G::VX], pub[G::VX];
             if (KIND == FK_FLUX) {
-                const T* CE = tileC(0);
-                const T* CN = tileC(1);
-                const T* RA = tileC(2);
+                const T* CE = tileC(0) + off0 + q * G::TW;
+                const T* CN = tileC(1) + off0 + q * G::TW;
+                const T* RA = tileC(2) + off0 + q * G::TW;
                 T ce[G::VX], cn[G::VX], cs[G::VX], ra[G::VX];
-                Ld<T, G::VX>::go(CE + lr * G::TW + lc0, ce);
-                const T cew = CE[lr * G::TW + iw];
-                Ld<T, G::VX>::go(CN + lr * G::TW + lc0, cn);
-                if (have_prev) {
+                Ld<T, G::VX>::go(CE, ce);
+                const T cew = *(CE - (lc0 > 0 ? 1 : 0));
+                Ld<T, G::VX>::go(CN, cn);
+                if ((ALLROWS && q > 0) || have_prev) {
 #pragma unroll
                     for (int v = 0; v < G::VX; ++v) cs[v] = cn_prev[v];
                 } else {
-                    Ld<T, G::VX>::go(CN + (lr - 1) * G::TW + lc0, cs);
+                    Ld<T, G::VX>::go(CN - G::TW, cs);
                 }
-                Ld<T, G::VX>::go(RA + lr * G::TW + lc0, ra);
+                Ld<T, G::VX>::go(RA, ra);
 #pragma unroll
                 for (int v = 0; v < G::VX; ++v) {
-                    const T o_e = v == G::VX - 1 ? oe : o[q][v + 1];
-                    const T o_w = v == 0 ? ow : o[q][v - 1];
+                    const T o_e = v == G::VX - 1 ? oe : o[q][v + 1 < G::VX ? v + 1 : v];
+                    const T o_w = v == 0 ? ow : o[q][v > 0 ? v - 1 : 0];
                     const T o_n = q == G::R - 1 ? on[v] : o[q + 1 < G::R ? q + 1 : q][v];
                     const T o_s = q == 0 ? os[v] : o[q > 0 ? q - 1 : 0][v];
-                    const T lap = flux_lap<T>(o[q][v], o_w, o_e, o_n, o_s, ce[v], v == 0 ? cew : ce[v - 1], cn[v],
-                                              cs[v], ra[v]);
-                    const T a = -st.t1[q][v] - c * lap;  // filter.py:171
-                    t0[v] = T(2) * a - st.t2[q][v];      // filter.py:197-203
+                    const T lap = flux_lap<T>(o[q][v], o_w, o_e, o_n, o_s, ce[v], v == 0 ? cew : ce[v > 0 ? v - 1 : 0],
+                                              cn[v], cs[v], ra[v]);
+                    const T a = -X1[q][v] - c * lap;  // filter.py:171
+                    t0[v] = T(2) * a - X2[q][v];      // filter.py:197-203
                     cn_prev[v] = cn[v];
                 }
                 have_prev = true;
             } else {
 #pragma unroll
                 for (int v = 0; v < G::VX; ++v) {
-                    const T o_e = v == G::VX - 1 ? oe : o[q][v + 1];
-                    const T o_w = v == 0 ? ow : o[q][v - 1];
+                    const T o_e = v == G::VX - 1 ? oe : o[q][v + 1 < G::VX ? v + 1 : v];
+                    const T o_w = v == 0 ? ow : o[q][v > 0 ? v - 1 : 0];
                     const T o_n = q == G::R - 1 ? on[v] : o[q + 1 < G::R ? q + 1 : q][v];
                     const T o_s = q == 0 ? os[v] : o[q > 0 ? q - 1 : 0][v];
                     const int idx = q * G::VX + v;
@@ -318,18 +324,32 @@ template <typename T, int KIND> struct FusedTile {
                     } else {       // kernels.py:115-121
                         lap = (((T(-4) * o[q][v] + o_e) + o_w) + o_n) + o_s;
                     }
-                    const T a = -st.t1[q][v] - c * lap;
-                    t0[v] = T(2) * a - st.t2[q][v];
+                    const T a = -X1[q][v] - c * lap;
+                    t0[v] = T(2) * a - X2[q][v];
                 }
             }
 #pragma unroll
             for (int v = 0; v < G::VX; ++v) {
                 st.acc[q][v] = (T)((double)st.acc[q][v] + pk * (double)t0[v]);  // filter.py:204
-                st.t2[q][v] = st.t1[q][v];                                      // pointer rotation, in registers
-                st.t1[q][v] = t0[v];
+                X2[q][v] = t0[v];                                               // T_i replaces T_{i-2}
                 pub[v] = sanitize(t0[v], (st.mbits >> (q * G::VX + v)) & 1u);
             }
-            St<T, G::VX>::go(D + lr * G::TW + lc0, pub);
+            St<T, G::VX>::go(D + off0 + q * G::TW, pub);
+        }
+    }
+
+    // odd steps read T_{i-1} from st.t1 and overwrite st.t2; even steps the other way round
+    GCMF_HD void step(int tid, int s, FusedThread<T>& st) const {
+        const int tx = tid % G::NTX, ty = tid / G::NTX;
+        const int lc0 = tx * G::VX;
+        if (lc0 + G::VX <= s || lc0 >= G::TW - s) return;  // column group outside the region
+        const bool inner = ty > 0 && ty < G::NTY - 1;      // G::R >= H: rows of inner threads are always inside
+        if (s & 1) {
+            if (inner) step_rows<true>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
+            else step_rows<false>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
+        } else {
+            if (inner) step_rows<true>(tid, s, tileS(1), tileS(0), st.t2, st.t1, st);
+            else step_rows<false>(tid, s, tileS(1), tileS(0), st.t2, st.t1, st);
         }
     }
 
@@ -344,8 +364,11 @@ template <typename T, int KIND> struct FusedTile {
             const int lr = ty * G::R + q;
             if (!owns_row(lr)) continue;
             const int gy = cy0 + lr - G::H;
-            St<T, G::VX>::go(P.t1_out.p + level * P.t1_out.bstride + (int64_t)gy * P.t1_out.pitch + gx, st.t1[q]);
-            St<T, G::VX>::go(P.t2_out.p + level * P.t2_out.bstride + (int64_t)gy * P.t2_out.pitch + gx, st.t2[q]);
+            // after an odd number of steps the newest T sits in st.t2 (see step())
+            St<T, G::VX>::go(P.t1_out.p + level * P.t1_out.bstride + (int64_t)gy * P.t1_out.pitch + gx,
+                             (P.k & 1) ? st.t2[q] : st.t1[q]);
+            St<T, G::VX>::go(P.t2_out.p + level * P.t2_out.bstride + (int64_t)gy * P.t2_out.pitch + gx,
+                             (P.k & 1) ? st.t1[q] : st.t2[q]);
             St<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)gy * P.bar.pitch + gx, st.acc[q]);
         }
     }
@@ -397,8 +420,7 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
         }
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {
-            if (s & 1) tl.step(tid, s, tl.tileS(0), tl.tileS(1), st);
-            else tl.step(tid, s, tl.tileS(1), tl.tileS(0), st);
+            tl.step(tid, s, st);
             __syncthreads();
         }
         tl.store(tid, l, st);

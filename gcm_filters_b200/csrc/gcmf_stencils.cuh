@@ -27,31 +27,38 @@ template <typename T> struct Lim;
 template <> struct Lim<float> { static GCMF_HD float big() { return 3.402823466e+38f; } };
 template <> struct Lim<double> { static GCMF_HD double big() { return 1.7976931348623157e+308; } };
 
-// numpy.nan_to_num: NaN -> 0, +-inf -> +-largest finite value.  Finite values (the hot case) cost
-// one exponent test; NaN / inf take the rare branch.
+// numpy.nan_to_num: NaN -> 0, +-inf -> +-largest finite value.  Branch-free on the device (integer
+// selects on the bit pattern) so that it never splits a warp or blocks instruction scheduling.
 GCMF_HD double nan2num(double x) {
 #ifdef __CUDA_ARCH__
-    const unsigned hi = (unsigned)__double2hiint(x);
-    if ((hi & 0x7ff00000u) == 0x7ff00000u) {
+    const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
+    const bool nonfin = (hi & 0x7ff00000u) == 0x7ff00000u;
+    const bool isnan = ((hi & 0x000fffffu) | lo) != 0u;  // only meaningful when nonfin
+    const unsigned fhi = isnan ? 0u : ((hi & 0x80000000u) | 0x7fefffffu);
+    const unsigned flo = isnan ? 0u : 0xffffffffu;
+    return __hiloint2double((int)(nonfin ? fhi : hi), (int)(nonfin ? flo : lo));
 #else
     if (!(x - x == 0.0)) {
-#endif
         if (x != x) return 0.0;
         return x > 0.0 ? Lim<double>::big() : -Lim<double>::big();
     }
     return x;
+#endif
 }
 GCMF_HD float nan2num(float x) {
 #ifdef __CUDA_ARCH__
     const unsigned u = __float_as_uint(x);
-    if ((u & 0x7f800000u) == 0x7f800000u) {
+    const bool nonfin = (u & 0x7f800000u) == 0x7f800000u;
+    const bool isnan = (u & 0x007fffffu) != 0u;
+    const unsigned f = isnan ? 0u : ((u & 0x80000000u) | 0x7f7fffffu);
+    return __uint_as_float(nonfin ? f : u);
 #else
     if (!(x - x == 0.0f)) {
-#endif
         if (x != x) return 0.0f;
         return x > 0.0f ? Lim<float>::big() : -Lim<float>::big();
     }
     return x;
+#endif
 }
 
 struct PlaneRef {
