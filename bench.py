@@ -312,23 +312,25 @@ def gpu_arm(args):
         if area:
             lib.prepare(plan.handle, nb, X, B, sptr)
             X = B
-        timed("first", 1, lambda: lib.cheb_step(plan.handle, nb, 1, X, None, A, outs, sptr))
-        T1, T2 = A, X
-        i = 2
-        while i <= n_steps:
-            if kfuse and i < n_steps:
-                kk = min(n_steps - i, kfuse)
-                in_ab = T1[0][0] in (A[0][0], B[0][0])
-                O1, O2 = (bufs[2], bufs[3]) if in_ab else (A, B)
+        if kfuse:  # same blocks as gcmf_filter: ceil(n/kfuse) fused launches, first/last steps included
+            cur = 1 if area else 0
+            T1, T2 = X, X
+            i = 1
+            while i <= n_steps:
+                kk = min(n_steps - i + 1, kfuse)
+                O1, O2 = bufs[2 * cur], bufs[2 * cur + 1]
                 timed("fused", kk, lambda: lib.cheb_fused(plan.handle, nb, i, kk, T1, T2, O1, O2, outs, sptr))
                 T1, T2 = O1, O2
+                cur ^= 1
                 i += kk
-                continue
+            continue
+        timed("first", 1, lambda: lib.cheb_step(plan.handle, nb, 1, X, None, A, outs, sptr))
+        T1, T2 = A, X
+        for i in range(2, n_steps + 1):
             D = B if (i == 2 and not area) else T2
             timed("mid" if i < n_steps else "last", 1,
                   lambda: lib.cheb_step(plan.handle, nb, i, T1, T2, D, outs, sptr))
             T2, T1 = T1, D
-            i += 1
     torch.cuda.synchronize(dev)
     per_kind = {}
     for kind, k, e0, e1 in records:
@@ -340,7 +342,7 @@ def gpu_arm(args):
     peak, peak_src = measured_hbm_peak()
     # algorithmic bytes of one launch = B_alg per grid-point step x points x steps the launch performs
     achieved = b_alg * nb * ny * nx * dom[1] / (dom_ms * 1e-3) / 1e9
-    kname = {"fused": f"fused_flux_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)",
+    kname = {"fused": f"fused_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)",
              "mid": "step_kernel<MODE_MID> (one Chebyshev step)", "first": "step_kernel<MODE_FIRST>",
              "last": "step_kernel<MODE_LAST>"}[dom[0]]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

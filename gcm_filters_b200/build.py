@@ -12,7 +12,7 @@ HEADERS = ["gcmf_stencils.cuh", "gcmf_internal.h", os.path.join("..", "..", "inc
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",  # separate rounding of * and +, in the reference's evaluation order
-    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-diag-suppress", "128",
 ]
 
 

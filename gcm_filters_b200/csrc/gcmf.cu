@@ -487,12 +487,17 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
                        const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st) {
     using G = FusedGeom<T>;
     const int kind = fused_kind_t<T>(pl);
-    const gcmf_field* all[5] = {t1, t2, t1o, t2o, bar};
+    const bool first = step0 == 1, last = step0 + k - 1 == pl->n_steps;
+    const gcmf_field* all[5] = {t1, first ? nullptr : t2, last ? nullptr : t1o, last ? nullptr : t2o, bar};
     for (const gcmf_field* f : all)
-        if (!aligned(f->ptr, f->pitch, f->bstride, G::VX, sizeof(T)))
+        if (f && !aligned(f->ptr, f->pitch, f->bstride, G::VX, sizeof(T)))
             return gcmf_set_error(GCMF_EINVAL, "fused step: fields must be 16-byte aligned with vector-multiple strides");
-    if (t1o->ptr == t1->ptr || t1o->ptr == t2->ptr || t2o->ptr == t1->ptr || t2o->ptr == t2->ptr)
+    if (!last && (t1o->ptr == t1->ptr || t2o->ptr == t1->ptr || (!first && (t1o->ptr == t2->ptr || t2o->ptr == t2->ptr))))
         return gcmf_set_error(GCMF_EINVAL, "fused step: outputs must not alias inputs (neighbouring tiles read them)");
+    if (bar->ptr == t1->ptr) return gcmf_set_error(GCMF_EINVAL, "fused step: bar must not alias the input");
+    if (last && (pl->desc.flags & GCMF_FLAG_AREA) &&
+        (pl->plane[1].nb != 1 || !aligned(pl->plane[1].p, pl->plane[1].pitch, 0, G::VX, sizeof(T))))
+        return gcmf_set_error(GCMF_EINVAL, "fused step: the area plane must be a shared, vector-aligned 2-D plane");
     FusedParams<T> P;
     memset(&P, 0, sizeof P);
     P.g.ny = pl->desc.ny;
@@ -500,9 +505,14 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
     P.g.flags = pl->desc.flags;
     for (int s = 0; s < 3; ++s) P.plane[s] = pl->plane[s];
     P.t1_in = FieldRef<const T>{(const T*)t1->ptr, t1->pitch, t1->bstride};
-    P.t2_in = FieldRef<const T>{(const T*)t2->ptr, t2->pitch, t2->bstride};
-    P.t1_out = FieldRef<T>{(T*)t1o->ptr, t1o->pitch, t1o->bstride};
-    P.t2_out = FieldRef<T>{(T*)t2o->ptr, t2o->pitch, t2o->bstride};
+    if (!first) P.t2_in = FieldRef<const T>{(const T*)t2->ptr, t2->pitch, t2->bstride};
+    if (!last) {
+        P.t1_out = FieldRef<T>{(T*)t1o->ptr, t1o->pitch, t1o->bstride};
+        P.t2_out = FieldRef<T>{(T*)t2o->ptr, t2o->pitch, t2o->bstride};
+    }
+    P.first = first;
+    P.last = last;
+    P.p0 = pl->p[0];
     P.bar = FieldRef<T>{(T*)bar->ptr, bar->pitch, bar->bstride};
     P.c = pl->c;
     for (int s = 0; s < k; ++s) P.p[s] = pl->p[step0 + s];
@@ -510,9 +520,9 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
     P.ncx = (pl->desc.nx + G::CW - 1) / G::CW;
     P.ncy = (pl->desc.ny + G::CH - 1) / G::CH;
     P.nb = nb;
-    // level slabs: one CTA keeps its coefficient tiles for a whole slab; aim for >= 8 waves of CTAs
+    // level slabs: one CTA keeps its coefficient tiles for a whole slab; aim for >= 40 waves of CTAs (tail < 3 %)
     const int64_t ntiles = (int64_t)P.ncx * P.ncy;
-    int64_t groups = (8LL * pl->sm_count + ntiles - 1) / ntiles;
+    int64_t groups = (40LL * pl->sm_count + ntiles - 1) / ntiles;
     if (groups < 1) groups = 1;
     if (groups > nb) groups = nb;
     P.levels_per_cta = (int32_t)((nb + groups - 1) / groups);
@@ -543,14 +553,15 @@ extern "C" int gcmf_cheb_fused(gcmf_plan* p, int64_t nb, int32_t step, int32_t k
     if (p->n_steps < 2) return gcmf_set_error(GCMF_ESTATE, "gcmf_plan_set_filter has not been called");
     if (!fused_eligible(p)) return gcmf_set_error(GCMF_EINVAL, "this plan has no fused path (see gcmf_fused_max_steps)");
     if (k < 1 || k > FusedGeom<double>::H) return gcmf_set_error(GCMF_EINVAL, "k = %d outside 1..%d", k, FusedGeom<double>::H);
-    if (step < 2 || step + k - 1 >= p->n_steps)
-        return gcmf_set_error(GCMF_EINVAL, "fused steps %d..%d must lie strictly inside 2..%d", step, step + k - 1,
-                              p->n_steps - 1);
+    if (step < 1 || step + k - 1 > p->n_steps)
+        return gcmf_set_error(GCMF_EINVAL, "fused steps %d..%d must lie inside 1..%d", step, step + k - 1, p->n_steps);
     TRY(check_planes(p));
     TRY(check_fields(p, t1_in, "t1_in"));
-    TRY(check_fields(p, t2_in, "t2_in"));
-    TRY(check_fields(p, t1_out, "t1_out"));
-    TRY(check_fields(p, t2_out, "t2_out"));
+    if (step > 1) TRY(check_fields(p, t2_in, "t2_in"));
+    if (step + k - 1 < p->n_steps) {
+        TRY(check_fields(p, t1_out, "t1_out"));
+        TRY(check_fields(p, t2_out, "t2_out"));
+    }
     TRY(check_fields(p, bar, "bar"));
     CUDA_TRY(cudaSetDevice(p->desc.device));
     if (p->desc.dtype == GCMF_F64)
@@ -586,33 +597,35 @@ extern "C" int gcmf_filter(gcmf_plan* p, int64_t nb, const gcmf_field* in, const
         TRY(gcmf_prepare(p, nb, in, B, stream));
         for (int k = 0; k < nc; ++k) X[k] = B[k];
     }
+    const int n = p->n_steps;
+    if (plan_uses_fused(p)) {
+        // Temporally blocked path: the whole recurrence (filter.py:191-206) as ceil(n/kmax) launches; the first
+        // block performs step 1, the last one finalizes bar.  State ping-pongs between two workspace pairs.
+        const int kmax = p->steps_per_block ? p->steps_per_block : FusedGeom<double>::H;
+        gcmf_field pair[2][2] = {{A[0], B[0]},
+                                 {gcmf_field{(char*)workspace + (size_t)2 * bb, pitch, bs},
+                                  gcmf_field{(char*)workspace + (size_t)3 * bb, pitch, bs}}};
+        int cur = area ? 1 : 0;  // the prepared field lives in B (pair 0) when area-weighted
+        gcmf_field T1 = X[0], T2 = X[0];
+        for (int i = 1; i <= n;) {
+            const int kk = (n - i + 1) < kmax ? (n - i + 1) : kmax;
+            TRY(gcmf_cheb_fused(p, nb, i, kk, &T1, &T2, &pair[cur][0], &pair[cur][1], out, stream));
+            T1 = pair[cur][0];
+            T2 = pair[cur][1];
+            cur ^= 1;
+            i += kk;
+        }
+        return GCMF_OK;
+    }
     // step 1: T1 = A(x) -> A ; bar = p0 x + p1 T1 -> out        (filter.py:191-195)
     TRY(gcmf_cheb_step(p, nb, 1, X, nullptr, A, out, stream));
     gcmf_field T1[2], T2[2];
     for (int k = 0; k < nc; ++k) { T1[k] = A[k]; T2[k] = X[k]; }
-    int i = 2;
-    const int n = p->n_steps;
-    const bool fuse = plan_uses_fused(p);
-    while (i <= n) {  // filter.py:196-206; pointer rotation replaces the two .copy() per step
-        const int kmax = p->steps_per_block ? p->steps_per_block : FusedGeom<double>::H;
-        // fused blocks cover the mid steps 2..n-1 (step 2 reads the prepared input as T2, never writes it)
-        if (fuse && i < n) {
-            const int kk = (n - i) < kmax ? (n - i) : kmax;  // steps i .. i+kk-1 <= n-1
-            // ping-pong between the two workspace pairs: (A,B) <-> (C,D)
-            gcmf_field C{(char*)workspace + (size_t)2 * bb, pitch, bs}, D{(char*)workspace + (size_t)3 * bb, pitch, bs};
-            const bool in_ab = (T1[0].ptr == A[0].ptr || T1[0].ptr == B[0].ptr);
-            gcmf_field O1 = in_ab ? C : A[0], O2 = in_ab ? D : B[0];
-            TRY(gcmf_cheb_fused(p, nb, i, kk, &T1[0], &T2[0], &O1, &O2, out, stream));
-            T1[0] = O1;
-            T2[0] = O2;
-            i += kk;
-            continue;
-        }
+    for (int i = 2; i <= n; ++i) {  // filter.py:196-206; pointer rotation replaces the two .copy() per step
         gcmf_field Dst[2];
         for (int k = 0; k < nc; ++k) Dst[k] = (i == 2 && !area) ? B[k] : T2[k];  // never write the user's input
         TRY(gcmf_cheb_step(p, nb, i, T1, T2, Dst, out, stream));
         for (int k = 0; k < nc; ++k) { T2[k] = T1[k]; T1[k] = Dst[k]; }
-        ++i;
     }
     return GCMF_OK;
 }

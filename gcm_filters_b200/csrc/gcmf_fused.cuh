@@ -61,6 +61,9 @@ template <typename T> struct FusedParams {
     double c;
     double p[FusedGeom<T>::H];  // Chebyshev coefficients of the k steps
     int32_t k;                  // fused steps, 1..H
+    int32_t first;              // block starts at recurrence step 1: t1_in = prepared field x, no T_{i-2}, no bar yet
+    int32_t last;               // block ends at step n_steps: bar is finalized (/area) and no T is stored
+    double p0;                  // p[0] (first block)
     int32_t ncx, ncy;           // core tiles along x / y
     int64_t nb;                 // batch slices
     int32_t levels_per_cta;
@@ -77,16 +80,6 @@ template <typename T> struct FusedThread {  // per-thread registers that live ac
 GCMF_HD int wrap_index(int v, int n) {
     v %= n;
     return v < 0 ? v + n : v;
-}
-
-// One flux-form Laplacian value (same expression as OpFlux::apply; kernels.py:297-315, 564-585).
-template <typename T>
-GCMF_HD T flux_lap(T oc, T ow, T oe, T on, T os, T ce, T cew, T cn, T cs, T ra) {
-    const T fe = (oe - oc) * ce;
-    const T fw = (oc - ow) * cew;
-    const T fn = (on - oc) * cn;
-    const T fs = (oc - os) * cs;
-    return (((fe - fw) + fn) - fs) * ra;
 }
 
 // ---- bulk async copy global -> shared, completing on an mbarrier (device) / memcpy (host emulator) ----
@@ -172,7 +165,7 @@ template <typename T, int KIND> struct FusedTile {
     // phase: thread r < TH issues row r of T1(level) -> X and T2(level) -> Y
     GCMF_HD void issue_state_row(int r, int64_t level, uint64_t* mb) const {
         copy_row(tileX(), P.t1_in.p + level * P.t1_in.bstride, P.t1_in.pitch, r, mb);
-        copy_row(tileY(), P.t2_in.p + level * P.t2_in.bstride, P.t2_in.pitch, r, mb);
+        if (!P.first) copy_row(tileY(), P.t2_in.p + level * P.t2_in.bstride, P.t2_in.pitch, r, mb);
     }
 
     GCMF_HD bool owns_cols(int tx) const {
@@ -216,7 +209,7 @@ template <typename T, int KIND> struct FusedTile {
 #pragma unroll
         for (int q = 0; q < G::R; ++q) {
             const int lr = ty * G::R + q;
-            if (oc && owns_row(lr)) {
+            if (oc && owns_row(lr) && !P.first) {
                 Ld<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)(cy0 + lr - G::H) * P.bar.pitch +
                                      (cx0 + lc0 - G::H), st.acc[q]);
             } else {
@@ -237,7 +230,12 @@ template <typename T, int KIND> struct FusedTile {
         for (int q = 0; q < G::R; ++q) {
             const int off = (ty * G::R + q) * G::TW + lc0;
             Ld<T, G::VX>::go(X + off, st.t1[q]);
-            Ld<T, G::VX>::go(Y + off, st.t2[q]);
+            if (!P.first) {
+                Ld<T, G::VX>::go(Y + off, st.t2[q]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < G::VX; ++v) st.t2[q][v] = T(0);
+            }
             T o[G::VX];
 #pragma unroll
             for (int v = 0; v < G::VX; ++v) o[v] = sanitize(st.t1[q][v], (st.mbits >> (q * G::VX + v)) & 1u);
@@ -261,11 +259,10 @@ template <typename T, int KIND> struct FusedTile {
         const T* Se = Sc + (lc0 + G::VX < G::TW ? G::VX : G::VX - 1);  // east neighbour of column lc0+VX-1 (clamped)
         const T c = (T)P.c;
         const double pk = P.p[s - 1];
+        const bool start = P.first && s == 1;  // recurrence step 1: T_1 = A(x), bar = p0 x + p1 T_1
         T o[G::R][G::VX], os[G::VX], on[G::VX];
 #pragma unroll
-        for (int q = 0; q < G::R; ++q)
-#pragma unroll
-            for (int v = 0; v < G::VX; ++v) o[q][v] = sanitize(X1[q][v], (st.mbits >> (q * G::VX + v)) & 1u);
+        for (int q = 0; q < G::R; ++q) Ld<T, G::VX>::go(Sc + q * G::TW, o[q]);  // = sanitize(X1), published by this thread
         if (ALLROWS || lr0 > 0) Ld<T, G::VX>::go(Sc - G::TW, os);
         if (ALLROWS || lr0 + G::R < G::TH) Ld<T, G::VX>::go(Sc + G::R * G::TW, on);
         T cn_prev[G::VX];
@@ -303,8 +300,8 @@ template <typename T, int KIND> struct FusedTile {
                     const T o_s = q == 0 ? os[v] : o[q > 0 ? q - 1 : 0][v];
                     const T lap = flux_lap<T>(o[q][v], o_w, o_e, o_n, o_s, ce[v], v == 0 ? cew : ce[v > 0 ? v - 1 : 0],
                                               cn[v], cs[v], ra[v]);
-                    const T a = -X1[q][v] - c * lap;  // filter.py:171
-                    t0[v] = T(2) * a - X2[q][v];      // filter.py:197-203
+                    const T a = shifted_flux<T>(X1[q][v], c, lap);  // filter.py:171
+                    t0[v] = start ? a : T(2) * a - X2[q][v];        // filter.py:192-194 / 197-203
                     cn_prev[v] = cn[v];
                 }
                 have_prev = true;
@@ -325,12 +322,13 @@ template <typename T, int KIND> struct FusedTile {
                         lap = (((T(-4) * o[q][v] + o_e) + o_w) + o_n) + o_s;
                     }
                     const T a = -X1[q][v] - c * lap;
-                    t0[v] = T(2) * a - X2[q][v];
+                    t0[v] = start ? a : T(2) * a - X2[q][v];
                 }
             }
 #pragma unroll
             for (int v = 0; v < G::VX; ++v) {
-                st.acc[q][v] = (T)((double)st.acc[q][v] + pk * (double)t0[v]);  // filter.py:204
+                st.acc[q][v] = start ? (T)(P.p0 * (double)X1[q][v] + pk * (double)t0[v])   // filter.py:195
+                                     : (T)((double)st.acc[q][v] + pk * (double)t0[v]);     // filter.py:204
                 X2[q][v] = t0[v];                                               // T_i replaces T_{i-2}
                 pub[v] = sanitize(t0[v], (st.mbits >> (q * G::VX + v)) & 1u);
             }
@@ -364,12 +362,24 @@ template <typename T, int KIND> struct FusedTile {
             const int lr = ty * G::R + q;
             if (!owns_row(lr)) continue;
             const int gy = cy0 + lr - G::H;
-            // after an odd number of steps the newest T sits in st.t2 (see step())
-            St<T, G::VX>::go(P.t1_out.p + level * P.t1_out.bstride + (int64_t)gy * P.t1_out.pitch + gx,
-                             (P.k & 1) ? st.t2[q] : st.t1[q]);
-            St<T, G::VX>::go(P.t2_out.p + level * P.t2_out.bstride + (int64_t)gy * P.t2_out.pitch + gx,
-                             (P.k & 1) ? st.t1[q] : st.t2[q]);
-            St<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)gy * P.bar.pitch + gx, st.acc[q]);
+            T outv[G::VX];
+#pragma unroll
+            for (int v = 0; v < G::VX; ++v) outv[v] = st.acc[q][v];
+            if (P.last) {
+                if (P.g.flags & FL_AREA) {  // finalize: divide by the cell area (kernels.py:103-104)
+                    T ar[G::VX];
+                    Ld<T, G::VX>::go(reinterpret_cast<const T*>(P.plane[1].p) + (int64_t)gy * P.plane[1].pitch + gx, ar);
+#pragma unroll
+                    for (int v = 0; v < G::VX; ++v) outv[v] = outv[v] / ar[v];
+                }
+            } else {
+                // after an odd number of steps the newest T sits in st.t2 (see step())
+                St<T, G::VX>::go(P.t1_out.p + level * P.t1_out.bstride + (int64_t)gy * P.t1_out.pitch + gx,
+                                 (P.k & 1) ? st.t2[q] : st.t1[q]);
+                St<T, G::VX>::go(P.t2_out.p + level * P.t2_out.bstride + (int64_t)gy * P.t2_out.pitch + gx,
+                                 (P.k & 1) ? st.t1[q] : st.t2[q]);
+            }
+            St<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)gy * P.bar.pitch + gx, outv);
         }
     }
 };
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
             mbar_expect_tx(&mb[0], 3 * ROW_BYTES);
             tl.issue_coef_row(tid, &mb[0]);
         }
-        mbar_expect_tx(&mb[1], 2 * ROW_BYTES);
+        mbar_expect_tx(&mb[1], (P.first ? 1 : 2) * ROW_BYTES);
         tl.issue_state_row(tid, l0, &mb[1]);
     }
     tl.load_mask(tid, st);
@@ -415,13 +425,17 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
         __syncthreads();  // S0 complete; landing tiles consumed
         if (l + 1 < l1 && tid < G::TH) {  // next level's tiles fly during the k steps
             fence_proxy_async();
-            mbar_expect_tx(&mb[1], 2 * ROW_BYTES);
+            mbar_expect_tx(&mb[1], (P.first ? 1 : 2) * ROW_BYTES);
             tl.issue_state_row(tid, l + 1, &mb[1]);
         }
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {
             tl.step(tid, s, st);
+#ifndef GCMF_EXPERIMENT_NOSYNC
             __syncthreads();
+#else
+            __syncwarp();
+#endif
         }
         tl.store(tid, l, st);
     }

@@ -10,6 +10,7 @@
 // E = [j,i+1], W = [j,i-1], N = [j+1,i], S = [j-1,i]; x always wraps; y wraps when WRAP_Y is set,
 // otherwise rows -1 and ny are ghost rows that exist in memory (latitude-band decomposition).
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #ifndef GCMF_HD
@@ -192,6 +193,24 @@ template <typename S> GCMF_HD const S* plane_base(const PlaneRef& pl, int b) {
     return reinterpret_cast<const S*>(pl.p) + (int64_t)(pl.nb > 1 ? (int)((unsigned)b % (unsigned)pl.nb) : 0) * pl.bstride;
 }
 
+// One flux-form Laplacian value, shared by the one-step and the fused kernels:
+//   Lap = (Fe - Fw + Fn - Fs) * ra with F = difference * face coefficient (kernels.py:297-315, 564-585),
+// evaluated as a chain of fused multiply-adds (explicit fma: the library is built with -fmad=false so that
+// nothing else contracts).  The flux family is not bit-comparable with the reference anyway (the face
+// coefficients are precombined, SURVEY note N3: ~1e-16 relative); the fma chain is the more accurate form.
+GCMF_HD double fma_(double a, double b, double c) { return ::fma(a, b, c); }
+GCMF_HD float fma_(float a, float b, float c) { return ::fmaf(a, b, c); }
+template <typename T>
+GCMF_HD T flux_lap(T oc, T ow, T oe, T on, T os, T ce, T cew, T cn, T cs, T ra) {
+    T sum = (oe - oc) * ce;
+    sum = fma_(ow - oc, cew, sum);   // - (oc - ow) * cew
+    sum = fma_(on - oc, cn, sum);
+    sum = fma_(os - oc, cs, sum);    // - (oc - os) * cs
+    return sum * ra;
+}
+// shifted Laplacian A(x) = -x - c*Lap (filter.py:171) for the flux family: one fma
+template <typename T> GCMF_HD T shifted_flux(T x, T c, T lap) { return fma_(-c, lap, -x); }
+
 // =====================================================================================
 // Operators.  apply(P, q, lap, x): lap[c][v] = Laplacian at the VX points, x[c][v] = raw centre
 // values of P.t1 (NaNs kept: the reference's `-field` term uses the raw field, filter.py:171).
@@ -200,6 +219,7 @@ template <typename S> GCMF_HD const S* plane_base(const PlaneRef& pl, int b) {
 // ---- REGULAR5 (kernels.py:107-124 unmasked; :150-190 masked; :435-492 masked + fold) ----
 template <typename T, int VX, bool MASKED> struct OpRegular5 {
     static constexpr int NC = 1;
+    static constexpr bool FMA_SHIFT = false;
     static GCMF_HD void apply(const StepParams<T>& P, const Pt& q, T (&lap)[1][VX], T (&x)[1][VX]) {
         Nb<T, VX> f;
         load_nb<T, VX>(f, P.t1[0].p + (int64_t)q.b * P.t1[0].bstride, P.t1[0].pitch, q, P.g.nx);
@@ -238,6 +258,7 @@ template <typename T, int VX, bool MASKED> struct OpRegular5 {
 //      (kernels.py:297-315, 351-372, 408-429, 564-585 with precombined face coefficients) ----
 template <typename T, int VX> struct OpFlux {
     static constexpr int NC = 1;
+    static constexpr bool FMA_SHIFT = true;
     static GCMF_HD void apply(const StepParams<T>& P, const Pt& q, T (&lap)[1][VX], T (&x)[1][VX]) {
         Nb<T, VX> f;
         load_nb<T, VX>(f, P.t1[0].p + (int64_t)q.b * P.t1[0].bstride, P.t1[0].pitch, q, P.g.nx);
@@ -267,13 +288,10 @@ template <typename T, int VX> struct OpFlux {
         Ld<T, VX>::go(ra + (int64_t)q.j * P.plane[2].pitch + q.i0, rav);
 #pragma unroll
         for (int v = 0; v < VX; ++v) {
-            const T o_e = v == VX - 1 ? oe : oc[v + 1];
-            const T o_w = v == 0 ? ow : oc[v - 1];
-            const T fe = (o_e - oc[v]) * cev[v];
-            const T fw = (oc[v] - o_w) * (v == 0 ? cew : cev[v - 1]);
-            const T fn = (on[v] - oc[v]) * cnv[v];
-            const T fs = (oc[v] - os[v]) * csv[v];
-            lap[0][v] = (((fe - fw) + fn) - fs) * rav[v];
+            const T o_e = v == VX - 1 ? oe : oc[v + 1 < VX ? v + 1 : v];
+            const T o_w = v == 0 ? ow : oc[v > 0 ? v - 1 : 0];
+            lap[0][v] = flux_lap<T>(oc[v], o_w, o_e, on[v], os[v], cev[v], v == 0 ? cew : cev[v > 0 ? v - 1 : 0], cnv[v],
+                                    csv[v], rav[v]);
         }
     }
 };
@@ -281,6 +299,7 @@ template <typename T, int VX> struct OpFlux {
 // ---- VECTOR_B (kernels.py:740-837): 10-term sum, left to right ----
 template <typename T, int VX> struct OpVectorB {
     static constexpr int NC = 2;
+    static constexpr bool FMA_SHIFT = false;
     static GCMF_HD void apply(const StepParams<T>& P, const Pt& q, T (&lap)[2][VX], T (&x)[2][VX]) {
         Nb<T, VX> u, w;
         load_nb<T, VX>(u, P.t1[0].p + (int64_t)q.b * P.t1[0].bstride, P.t1[0].pitch, q, P.g.nx);
@@ -315,6 +334,7 @@ template <typename T, int VX> struct OpVectorB {
 template <typename T, int VX> struct OpVectorC {
     static_assert(VX == 1, "VECTOR_C is instantiated with one point per thread");
     static constexpr int NC = 2;
+    static constexpr bool FMA_SHIFT = false;
     // value of a field or plane at (j+dj, i+di), dj, di in {-1,0,1}: base[off.o[dj+1][di+1]]
     struct Off9 { int64_t o[3][3]; };
     static GCMF_HD Off9 offsets(int64_t pitch, const Pt& q) {
@@ -389,7 +409,8 @@ GCMF_HD void step_body(const StepParams<T>& P, int b, int j, int i0) {
         }
         T a[VX];
 #pragma unroll
-        for (int v = 0; v < VX; ++v) a[v] = -x[k][v] - c * lap[k][v];  // shifted Laplacian, filter.py:171/173
+        for (int v = 0; v < VX; ++v)  // shifted Laplacian, filter.py:171/173
+            a[v] = OP::FMA_SHIFT ? shifted_flux<T>(x[k][v], c, lap[k][v]) : (-x[k][v] - c * lap[k][v]);
         T* barp = P.bar[k].p + (int64_t)b * P.bar[k].bstride + (int64_t)j * P.bar[k].pitch + i0;
         if (MODE == MODE_FIRST) {
             St<T, VX>::go(P.t0[k].p + (int64_t)b * P.t0[k].bstride + (int64_t)j * P.t0[k].pitch + i0, a);

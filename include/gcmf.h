@@ -147,10 +147,11 @@ int gcmf_cheb_step(gcmf_plan *plan, int64_t nb, int32_t step, const gcmf_field *
  * per step).  gcmf_fused_max_steps: how many recurrence steps this plan can fuse into one HBM round
  * trip (0 = no fused path for this operator / grid; the one-step kernels are used).
  * gcmf_plan_set_steps_per_block: 0 = auto (default), 1 = never fuse, 2..4 = cap the block length.
- * gcmf_cheb_fused: steps step .. step+k-1 (all strictly between 1 and n_steps) in one launch:
- *   reads T_{step-1} (`t1_in`) and T_{step-2} (`t2_in`), writes T_{step+k-1} (`t1_out`) and
- *   T_{step+k-2} (`t2_out`), and adds sum_s p[s] T_s to `bar`.  Scalar operators only; outputs must
- *   not alias inputs (neighbouring tiles read the inputs' halos). */
+ * gcmf_cheb_fused: recurrence steps step .. step+k-1 (1 <= step, step+k-1 <= n_steps) in one launch:
+ *   reads T_{step-1} (`t1_in`; the prepared field when step == 1) and T_{step-2} (`t2_in`, ignored when
+ *   step == 1), writes T_{step+k-1} (`t1_out`) and T_{step+k-2} (`t2_out`) unless the block reaches
+ *   n_steps, and updates `bar` (initialised by step 1, finalized by step n_steps).  Scalar operators
+ *   only; outputs must not alias inputs (neighbouring tiles read the inputs' halos). */
 int gcmf_fused_max_steps(const gcmf_plan *plan);
 int gcmf_plan_set_steps_per_block(gcmf_plan *plan, int32_t k);
 int gcmf_cheb_fused(gcmf_plan *plan, int64_t nb, int32_t step, int32_t k, const gcmf_field *t1_in,

@@ -259,7 +259,7 @@ def test_fused_steps_equal_one_step_kernels(g, dtype, shape):
         capped = flt.apply(fb, None)
     finally:
         engine.set_steps_per_block(0)
-    assert n_plain == flt.n_steps and n_fused == 2 + -(-(flt.n_steps - 2) // 4)
+    assert n_plain == flt.n_steps and n_fused == -(-flt.n_steps // 4)
     assert np.array_equal(fused, plain, equal_nan=True)
     assert np.array_equal(capped, plain, equal_nan=True)
     ref = np_oracle.apply_filter(g, gv, (fb.astype(np.float64),), filter_scale=10.0, dx_min=1.0)

@@ -32,7 +32,7 @@ def test_fused_equals_unfused_f64(g, shape, nb, n_steps):
     n0 = fused.lib.launch_count()
     (a,) = fused.filter((fb,), spec.p, c)
     launches = fused.lib.launch_count() - n0
-    assert launches == 2 + -(-(n_steps - 2) // 4)  # first + last + ceil(mid/4) fused blocks
+    assert launches == -(-n_steps // 4)  # the whole recurrence in ceil(n/4) fused launches
     plain = EmuPlan(lap, np.float64, *shape)
     emu_set_steps_per_block(plain, 1)
     (b,) = plain.filter((fb,), spec.p, c)
@@ -94,7 +94,7 @@ def test_fused_regular5(g, dtype, shape):
     assert fused.lib.fused_max_steps(fused.h) == 4
     n0 = fused.lib.launch_count()
     (a,) = fused.filter((fb.astype(dtype),), spec.p, c)
-    assert fused.lib.launch_count() - n0 == 2 + 3 + (1 if "AREA" in g else 0)
+    assert fused.lib.launch_count() - n0 == 3 + (1 if "AREA" in g else 0)  # ceil(11/4) (+ prepare)
     plain = EmuPlan(lap, dtype, *shape)
     emu_set_steps_per_block(plain, 1)
     (b,) = plain.filter((fb.astype(dtype),), spec.p, c)
