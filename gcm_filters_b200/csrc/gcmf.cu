@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -439,7 +440,7 @@ static int fused_kind(const gcmf_plan* p) {
 static bool fused_eligible(const gcmf_plan* p) { return fused_kind(p) >= 0; }
 
 #ifdef GCMF_HOSTEMU
-template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, int ncta) {
+template <typename T, int KIND, bool EDGE> static void fused_host_t(const FusedParams<T>& P, int ncta) {
     using G = FusedGeom<T>;
     std::vector<T> smem((size_t)G::ntiles(KIND) * G::PLANE);
     std::vector<FusedThread<T>> st(G::NTHREADS);
@@ -450,7 +451,7 @@ template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, 
         const int64_t l1 = l0 + P.levels_per_cta < P.nb ? l0 + P.levels_per_cta : P.nb;
         if (l0 >= l1) continue;
         for (auto& v : smem) v = T(12345);
-        FusedTile<T, KIND> tl(P, tile, smem.data());
+        FusedTile<T, KIND, EDGE> tl(P, tile, smem.data());
         for (int r = 0; r < G::TH; ++r) {
             if (KIND == FK_FLUX) tl.issue_coef_row(r, nullptr);
             tl.issue_state_row(r, l0, nullptr);
@@ -466,19 +467,28 @@ template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, 
         }
     }
 }
+template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, int ncta) {
+    if (P.first || P.last) fused_host_t<T, KIND, true>(P, ncta);
+    else fused_host_t<T, KIND, false>(P, ncta);
+}
 #else
-template <typename T, int KIND> static int launch_fused_kernel(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
+template <typename T, int KIND, bool EDGE>
+static int launch_fused_kernel_t(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
     using G = FusedGeom<T>;
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(fused_kernel<T, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(fused_kernel<T, KIND, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)G::smem_bytes(KIND)));
         attr_done = true;
     }
-    fused_kernel<T, KIND><<<(unsigned)ncta, G::NTHREADS, G::smem_bytes(KIND), st>>>(P);
+    fused_kernel<T, KIND, EDGE><<<(unsigned)ncta, G::NTHREADS, G::smem_bytes(KIND), st>>>(P);
     gcmf_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return GCMF_OK;
+}
+template <typename T, int KIND> static int launch_fused_kernel(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
+    if (P.first || P.last) return launch_fused_kernel_t<T, KIND, true>(P, ncta, st);
+    return launch_fused_kernel_t<T, KIND, false>(P, ncta, st);
 }
 #endif
 
@@ -522,7 +532,12 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
     P.nb = nb;
     // level slabs: one CTA keeps its coefficient tiles for a whole slab; aim for >= 40 waves of CTAs (tail < 3 %)
     const int64_t ntiles = (int64_t)P.ncx * P.ncy;
-    int64_t groups = (40LL * pl->sm_count + ntiles - 1) / ntiles;
+    static const long long waves = [] {  // tuning knob: minimum number of CTA waves (default 40)
+        const char* e = getenv("GCMF_FUSED_WAVES");
+        const long long v = e ? atoll(e) : 0;
+        return v > 0 ? v : 40LL;
+    }();
+    int64_t groups = (waves * pl->sm_count + ntiles - 1) / ntiles;
     if (groups < 1) groups = 1;
     if (groups > nb) groups = nb;
     P.levels_per_cta = (int32_t)((nb + groups - 1) / groups);

@@ -47,7 +47,7 @@ template <typename T> struct FusedGeom {
     static constexpr int PLANE = TH * TW;           // elements per shared-memory tile (32 KiB)
     // tiles: X, Y (TMA landing of T1, T2), S0, S1 (sanitized ping-pong) [+ ce, cn, ra for FLUX]
     static GCMF_HD constexpr int ntiles(int kind) { return kind == FK_FLUX ? 7 : 4; }
-    static GCMF_HD constexpr size_t smem_bytes(int kind) { return (size_t)ntiles(kind) * PLANE * sizeof(T) + 64; }
+    static GCMF_HD constexpr size_t smem_bytes(int kind) { return (size_t)ntiles(kind) * PLANE * sizeof(T) + 256; }
 };
 
 template <typename T> struct FusedParams {
@@ -102,6 +102,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, unsigned parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(mb)), "r"(parity) : "memory");
 }
+// ---- warp-to-warp progress flags in shared memory (release / acquire at CTA scope) ----
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t atom_add_acqrel_u32(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 #endif
@@ -120,13 +134,16 @@ GCMF_HD void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
 #endif
 }
 
-template <typename T, int KIND> struct FusedTile {
+// EDGE = false: a block strictly inside the recurrence (P.first and P.last are known to be 0 at compile time)
+template <typename T, int KIND, bool EDGE> struct FusedTile {
     using G = FusedGeom<T>;
     const FusedParams<T>& P;
     int gy0, gx0;      // global coordinates of tile element (0,0) (may be negative: wraps)
     int cy0, cx0;      // global coordinates of the first core element
     T* smem;
     bool masked;       // REG5 with a wet mask (nan_to_num + mask), else raw values (NaNs spread)
+    GCMF_HD bool is_first() const { return EDGE && P.first; }
+    GCMF_HD bool is_last() const { return EDGE && P.last; }
 
     GCMF_HD FusedTile(const FusedParams<T>& P_, int tile, T* smem_) : P(P_), smem(smem_) {
         const int cx = tile % P.ncx, cy = tile / P.ncx;
@@ -165,7 +182,7 @@ template <typename T, int KIND> struct FusedTile {
     // phase: thread r < TH issues row r of T1(level) -> X and T2(level) -> Y
     GCMF_HD void issue_state_row(int r, int64_t level, uint64_t* mb) const {
         copy_row(tileX(), P.t1_in.p + level * P.t1_in.bstride, P.t1_in.pitch, r, mb);
-        if (!P.first) copy_row(tileY(), P.t2_in.p + level * P.t2_in.bstride, P.t2_in.pitch, r, mb);
+        if (!is_first()) copy_row(tileY(), P.t2_in.p + level * P.t2_in.bstride, P.t2_in.pitch, r, mb);
     }
 
     GCMF_HD bool owns_cols(int tx) const {
@@ -209,7 +226,7 @@ template <typename T, int KIND> struct FusedTile {
 #pragma unroll
         for (int q = 0; q < G::R; ++q) {
             const int lr = ty * G::R + q;
-            if (oc && owns_row(lr) && !P.first) {
+            if (oc && owns_row(lr) && !is_first()) {
                 Ld<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)(cy0 + lr - G::H) * P.bar.pitch +
                                      (cx0 + lc0 - G::H), st.acc[q]);
             } else {
@@ -230,7 +247,7 @@ template <typename T, int KIND> struct FusedTile {
         for (int q = 0; q < G::R; ++q) {
             const int off = (ty * G::R + q) * G::TW + lc0;
             Ld<T, G::VX>::go(X + off, st.t1[q]);
-            if (!P.first) {
+            if (!is_first()) {
                 Ld<T, G::VX>::go(Y + off, st.t2[q]);
             } else {
 #pragma unroll
@@ -259,7 +276,7 @@ template <typename T, int KIND> struct FusedTile {
         const T* Se = Sc + (lc0 + G::VX < G::TW ? G::VX : G::VX - 1);  // east neighbour of column lc0+VX-1 (clamped)
         const T c = (T)P.c;
         const double pk = P.p[s - 1];
-        const bool start = P.first && s == 1;  // recurrence step 1: T_1 = A(x), bar = p0 x + p1 T_1
+        const bool start = is_first() && s == 1;  // recurrence step 1: T_1 = A(x), bar = p0 x + p1 T_1
         T o[G::R][G::VX], os[G::VX], on[G::VX];
 #pragma unroll
         for (int q = 0; q < G::R; ++q) Ld<T, G::VX>::go(Sc + q * G::TW, o[q]);  // = sanitize(X1), published by this thread
@@ -365,7 +382,7 @@ template <typename T, int KIND> struct FusedTile {
             T outv[G::VX];
 #pragma unroll
             for (int v = 0; v < G::VX; ++v) outv[v] = st.acc[q][v];
-            if (P.last) {
+            if (is_last()) {
                 if (P.g.flags & FL_AREA) {  // finalize: divide by the cell area (kernels.py:103-104)
                     T ar[G::VX];
                     Ld<T, G::VX>::go(reinterpret_cast<const T*>(P.plane[1].p) + (int64_t)gy * P.plane[1].pitch + gx, ar);
@@ -385,7 +402,7 @@ template <typename T, int KIND> struct FusedTile {
 };
 
 #ifdef __CUDACC__
-template <typename T, int KIND>
+template <typename T, int KIND, bool EDGE>
 __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const __grid_constant__ FusedParams<T> P) {
     using G = FusedGeom<T>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -398,24 +415,31 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
     const int64_t l0 = (int64_t)grp * P.levels_per_cta;
     const int64_t l1 = l0 + P.levels_per_cta < P.nb ? l0 + P.levels_per_cta : P.nb;
     if (l0 >= l1) return;
-    FusedTile<T, KIND> tl(P, tile, smem);
+    FusedTile<T, KIND, EDGE> tl(P, tile, smem);
     FusedThread<T> st;
+    const bool first = EDGE && P.first;
     constexpr unsigned ROW_BYTES = G::TW * sizeof(T);
     if (tid == 0) {
         mbar_init(&mb[0], G::TH);
         mbar_init(&mb[1], G::TH);
         fence_mbar_init();
     }
+    if (tid < 40) reinterpret_cast<uint32_t*>(mb + 2)[tid] = 0u;  // progress flags [32] + drain counter
+    static_assert(G::TH == 32, "the landing-tile refill is issued by one warp: one lane per tile row");
     __syncthreads();
     if (tid < G::TH) {
         if (KIND == FK_FLUX) {
             mbar_expect_tx(&mb[0], 3 * ROW_BYTES);
             tl.issue_coef_row(tid, &mb[0]);
         }
-        mbar_expect_tx(&mb[1], (P.first ? 1 : 2) * ROW_BYTES);
+        mbar_expect_tx(&mb[1], (first ? 1 : 2) * ROW_BYTES);
         tl.issue_state_row(tid, l0, &mb[1]);
     }
     tl.load_mask(tid, st);
+    // FLUX steps are long enough for neighbour-only synchronisation to pay; the light REGULAR5 steps keep
+    // the cheaper CTA barrier.
+    constexpr bool FINE_SYNC = KIND == FK_FLUX;
+    if (!FINE_SYNC) {
     int it = 0;
     for (int64_t l = l0; l < l1; ++l, ++it) {
         tl.load_bar(tid, l, st);
@@ -425,19 +449,71 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
         __syncthreads();  // S0 complete; landing tiles consumed
         if (l + 1 < l1 && tid < G::TH) {  // next level's tiles fly during the k steps
             fence_proxy_async();
-            mbar_expect_tx(&mb[1], (P.first ? 1 : 2) * ROW_BYTES);
+            mbar_expect_tx(&mb[1], (first ? 1 : 2) * ROW_BYTES);
             tl.issue_state_row(tid, l + 1, &mb[1]);
         }
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {
             tl.step(tid, s, st);
-#ifndef GCMF_EXPERIMENT_NOSYNC
             __syncthreads();
-#else
-            __syncwarp();
-#endif
         }
         tl.store(tid, l, st);
+    }
+    } else {
+    // Neighbour-only synchronisation instead of a CTA barrier per step.  A warp covers half a tile row
+    // group (32 threads x R rows); in phase g (g = it*(k+1) + s, s = 0 for extract) it reads rows published
+    // in phase g-1 by the warps above / below it and by the other half of its own rows, and overwrites
+    // rows those same warps read in phase g-1.  Both hazards are covered by one rule: start phase g only
+    // when these three warps have completed phase g-1.  Warps therefore drift apart by up to one phase per
+    // hop, which spreads shared-memory and fp64 work in time instead of convoying at a barrier.
+    uint32_t* prog = reinterpret_cast<uint32_t*>(mb + 2);  // [NWARPS] completed-phase counters
+    uint32_t* xcount = prog + 32;                           // warps that have drained the landing tiles
+    constexpr int NWARPS = G::NTHREADS / 32;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wy = warp >> 1, wh = warp & 1;
+    int nb_warp = -1;  // lanes 0..2 each watch one neighbour warp
+    if (lane == 0) nb_warp = wy * 2 + (wh ^ 1);
+    if (lane == 1 && wy > 0) nb_warp = (wy - 1) * 2 + wh;
+    if (lane == 2 && wy < G::NTY - 1) nb_warp = (wy + 1) * 2 + wh;
+    auto wait_neighbours = [&](uint32_t need) {
+        if (need == 0) return;
+        unsigned spins = 0;
+        while (true) {
+            const bool ok = nb_warp < 0 || ld_acquire_u32(&prog[nb_warp]) >= need;
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (++spins > (1u << 28)) asm volatile("trap;");  // a lost wake-up must not hang the GPU
+        }
+    };
+    auto publish = [&](uint32_t done) {
+        __syncwarp();
+        if (lane == 0) st_release_u32(&prog[warp], done);
+    };
+    int it = 0;
+    for (int64_t l = l0; l < l1; ++l, ++it) {
+        const uint32_t g0 = (uint32_t)it * (uint32_t)(P.k + 1);
+        tl.load_bar(tid, l, st);
+        if (KIND == FK_FLUX && it == 0) mbar_wait(&mb[0], 0);
+        mbar_wait(&mb[1], (unsigned)(it & 1));
+        wait_neighbours(g0);
+        tl.extract(tid, st);
+        publish(g0 + 1);
+        // the last warp to drain the landing tiles refills them for the next level (32 lanes = TH rows)
+        uint32_t old = 0;
+        if (lane == 0) old = atom_add_acqrel_u32(xcount, 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == (uint32_t)NWARPS * (uint32_t)(it + 1) - 1u && l + 1 < l1) {
+            fence_proxy_async();
+            mbar_expect_tx(&mb[1], (first ? 1 : 2) * ROW_BYTES);
+            tl.issue_state_row(lane, l + 1, &mb[1]);
+        }
+#pragma unroll 1
+        for (int s = 1; s <= P.k; ++s) {
+            wait_neighbours(g0 + (uint32_t)s);
+            tl.step(tid, s, st);
+            publish(g0 + (uint32_t)s + 1u);
+        }
+        tl.store(tid, l, st);
+    }
     }
 }
 #endif
