@@ -238,9 +238,125 @@ def run_laplacian(lap, fields):
     return st.deliver(outs)
 
 
+# Host-resident inputs are streamed through the device in batch chunks so that the H2D copy of chunk i+1,
+# the filter of chunk i and the D2H copy of chunk i-1 overlap (three streams, event-chained).  Copies are
+# truly asynchronous only from / to pinned memory (torch CPU tensors with pin_memory, or `out=` pinned).
+PIPELINE_MIN_CHUNKS = 4
+PIPELINE_TARGET_CHUNKS = 8
+PIPELINE_MAX_CHUNK_BYTES = 1 << 30
+_pipe_lock = threading.Lock()
+_pipe_state = {}
+
+
+def _host_view(f, nb, ny, nx):
+    """(nb, ny, nx) torch CPU view of a host array (numpy or torch), without copying when contiguous."""
+    import torch
+
+    if _is_torch(f):
+        return f.reshape((nb, ny, nx)) if f.is_contiguous() else f.contiguous().reshape((nb, ny, nx))
+    a = np.asarray(getattr(f, "values", f))
+    if not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    if not a.flags.writeable:
+        a = a.copy()
+    return torch.from_numpy(a.reshape((nb, ny, nx)))
+
+
+def _pipeline_chunk(nb, slice_bytes):
+    chunk = max(1, nb // PIPELINE_TARGET_CHUNKS)
+    chunk = min(chunk, max(1, PIPELINE_MAX_CHUNK_BYTES // max(1, slice_bytes)))
+    return chunk
+
+
+def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
+    torch = _torch()
+    ncomp = lap.ncomp
+    ny, nx = shape[-2:]
+    nb = int(np.prod(shape[:-2]))
+    device = torch.device("cuda", torch.cuda.current_device())
+    tdt = torch.float32 if np_dtype == np.float32 else torch.float64
+    host_in = [_host_view(f, nb, ny, nx) for f in fields]
+    kind_numpy = not _is_torch(fields[0])
+    if out is not None:
+        out = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+        results = list(out)
+        host_out = [_host_view(o, nb, ny, nx) for o in out]
+    else:
+        pin = _is_torch(fields[0]) and fields[0].is_pinned()
+        host_out = [torch.empty((nb, ny, nx), dtype=tdt, pin_memory=pin) for _ in range(ncomp)]
+        results = [h.reshape(shape).numpy() if kind_numpy else h.reshape(shape) for h in host_out]
+    for h in host_out:
+        if h.dtype != tdt:
+            raise ValueError(f"`out` must have dtype {tdt}")
+    chunk = _pipeline_chunk(nb, ny * nx * np_dtype.itemsize)
+    plan = device_plan(lap, device.index, np_dtype, ny, nx)
+    plan.set_filter(p, c)
+    nbuf = 2
+    key = (device.index, str(tdt), ncomp, chunk, ny, nx)
+    with _pipe_lock:
+        stt = _pipe_state.get(key)
+        if stt is None:
+            _pipe_state.clear()  # one cached pipeline geometry per process: bounded device memory
+            stt = _pipe_state[key] = {
+                "din": [[torch.empty((chunk, ny, nx), dtype=tdt, device=device) for _ in range(ncomp)] for _ in range(nbuf)],
+                "dout": [[torch.empty((chunk, ny, nx), dtype=tdt, device=device) for _ in range(ncomp)] for _ in range(nbuf)],
+                "h2d": torch.cuda.Stream(device), "d2h": torch.cuda.Stream(device),
+            }
+    din, dout, s_h2d, s_d2h = stt["din"], stt["dout"], stt["h2d"], stt["d2h"]
+    s_comp = torch.cuda.current_stream(device)
+    ws = workspace(device, plan.lib.workspace_bytes(plan.handle, chunk))
+    ev_h2d = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_comp = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_d2h = [torch.cuda.Event() for _ in range(nbuf)]
+    s_h2d.wait_stream(s_comp)
+    starts = list(range(0, nb, chunk))
+    for i, b0 in enumerate(starts):
+        n = min(chunk, nb - b0)
+        k = i % nbuf
+        with torch.cuda.stream(s_h2d):
+            if i >= nbuf:
+                s_h2d.wait_event(ev_comp[k])  # the filter that read this input buffer has finished
+            for cc in range(ncomp):
+                src = host_in[cc][b0:b0 + n]
+                if src.dtype != tdt:
+                    src = src.to(tdt)
+                din[k][cc][:n].copy_(src, non_blocking=True)
+            ev_h2d[k].record(s_h2d)
+        s_comp.wait_event(ev_h2d[k])
+        if i >= nbuf:
+            s_comp.wait_event(ev_d2h[k])  # the previous result in this output buffer has left the device
+        plan.lib.filter(plan.handle, n, _specs([t[:n] for t in din[k]]), _specs([t[:n] for t in dout[k]]),
+                        ws.data_ptr(), ws.numel(), s_comp.cuda_stream)
+        ev_comp[k].record(s_comp)
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(ev_comp[k])
+            for cc in range(ncomp):
+                host_out[cc][b0:b0 + n].copy_(dout[k][cc][:n], non_blocking=True)
+            ev_d2h[k].record(s_d2h)
+    s_d2h.synchronize()
+    s_comp.wait_stream(s_d2h)
+    return tuple(results)
+
+
 def run_filter(lap, p, c, fields, out=None):
     """filtered = filter_func(fields) on the GPU: prepare, n_steps Chebyshev steps, finalize."""
     torch = _torch()
+    f0 = fields[0]
+    on_host = (not _is_torch(f0)) or f0.device.type == "cpu"
+    if on_host and len(fields) == lap.ncomp and (out is None or not (_is_torch(out[0] if isinstance(out, (tuple, list)) else out)
+                                                                    and (out[0] if isinstance(out, (tuple, list)) else out).is_cuda)):
+        shape = tuple(f0.shape)
+        if len(shape) > 2:
+            nb = int(np.prod(shape[:-2]))
+            in_dtype = np.dtype(str(f0.dtype).replace("torch.", "")) if _is_torch(f0) else np.asarray(f0).dtype
+            if in_dtype.kind != "f" or in_dtype.itemsize not in (4, 8):
+                in_dtype = np.dtype(np.float64)
+            np_dtype = lap.compute_dtype(in_dtype)
+            shared_planes = all(np.ndim(pl) <= 2 for pl in lap._planes.planes if pl is not None) and \
+                (lap._planes.mask is None or np.ndim(lap._planes.mask) <= 2)
+            chunk = _pipeline_chunk(nb, shape[-2] * shape[-1] * np_dtype.itemsize)
+            if shared_planes and nb >= PIPELINE_MIN_CHUNKS * chunk and all(tuple(f.shape) == shape for f in fields):
+                return _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype)
     st = _Staged(lap, fields)
     plan = device_plan(lap, st.device.index, st.np_dtype, st.ny, st.nx)
     plan.check_batch(st.batch_shape)

@@ -58,6 +58,8 @@ def apply_batch_sharded(apply_fn, field, rank, world, gather=False, group=None):
 
     was_numpy = not engine._is_torch(local)
     t = torch.as_tensor(local)
+    if dist.get_backend(group) == "nccl" and not t.is_cuda:  # NCCL moves device memory only
+        t = t.cuda()
     smax = max(hi - lo for lo, hi in batch_slabs(nb, world))
     pad = torch.zeros((smax, ny, nx), dtype=t.dtype, device=t.device)
     pad[: b - a] = t

@@ -1,0 +1,75 @@
+"""Multi-GPU tests (need >= 2 CUDA devices; skipped otherwise): NCCL halo exchange of the latitude-band
+decomposition and batch sharding, against the single-GPU result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, g, shape, q):
+    import torch
+    import torch.distributed as dist
+    from gcm_filters_b200 import Filter, FilterShape, GridType
+    from gcm_filters_b200.scheduler import BandedFilter, apply_batch_sharded
+    from oracle import fixtures
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        fields, gv = fixtures.fixture(g, shape)
+        fields = tuple(np.stack([f, f * f, 1 - f]) for f in fields)
+        fa = dict(filter_scale=6.0, dx_min=1.0)
+        if g in fixtures.VECTOR_GRIDS:
+            dxm = float(min(gv["dxT"].min(), gv["dyT"].min()))
+            fa = dict(filter_scale=6.0 * dxm, dx_min=dxm)
+        flt = Filter(grid_type=GridType[g], grid_vars=gv, filter_shape=FilterShape.GAUSSIAN, **fa)
+        if len(fields) == 2:
+            single = flt.apply_to_vector(fields[0], fields[1], dims=["y", "x"])
+        else:
+            single = (flt.apply(fields[0], dims=["y", "x"]),)
+        outs, (j0, j1) = BandedFilter(flt, rank, world).apply(*fields)
+        ok = all(np.array_equal(o, s[..., j0:j1, :], equal_nan=True) for o, s in zip(outs, single))
+        # batch sharding with an all-gather of the slabs
+        full = (apply_batch_sharded(lambda a: flt.apply(a, None), fields[0], rank, world, gather=True)
+                if len(fields) == 1 else None)
+        ok2 = True if full is None else bool(np.array_equal(full, single[0], equal_nan=True))
+        q.put((rank, bool(ok), ok2))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("g", ["IRREGULAR_WITH_LAND", "TRIPOLAR_POP_WITH_LAND", "VECTOR_C_GRID"])
+def test_banded_and_sharded_match_single_gpu(g):
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, g, (90, 160), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = [q.get(timeout=10) for _ in range(world)]
+    assert all(r[1] and r[2] for r in res), res
