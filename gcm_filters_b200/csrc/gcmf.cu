@@ -181,7 +181,10 @@ constexpr int BX = 32, BY = 8;
 // from HBM once and hit in L2 for the other nb-1 slices.
 #ifndef GCMF_HOSTEMU
 template <typename T, int VX, class OP, int MODE>
-__global__ void __launch_bounds__(BX* BY) step_kernel(const __grid_constant__ StepParams<T> P, unsigned nxb) {
+#ifndef GCMF_STEP_MINBLOCKS
+#define GCMF_STEP_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(BX* BY, GCMF_STEP_MINBLOCKS) step_kernel(const __grid_constant__ StepParams<T> P, unsigned nxb) {
     unsigned bid = blockIdx.x;  // 32-bit decode: the grid has < 2^31 blocks
     const unsigned xb = bid % nxb;
     bid /= nxb;
@@ -418,8 +421,11 @@ template <typename T> static int fused_kind_t(const gcmf_plan* p) {
     using G = FusedGeom<T>;
     const int fl = p->desc.flags;
     if (p->desc.nx % G::VX || p->desc.nx < G::TW || p->desc.ny < G::TH) return -1;
+    const int tripolar = GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S;  // both or neither: a whole (un-banded) tripolar grid
+    if ((fl & tripolar) != 0 && (fl & tripolar) != tripolar) return -1;
+    const int base = fl & ~tripolar;
     if (p->desc.op == GCMF_OP_FLUX) {
-        if (fl != (GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM)) return -1;
+        if (base != (GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM)) return -1;
         for (int s = 0; s < 3; ++s)
             if (!p->plane[s].p || p->plane[s].nb != 1 ||
                 !aligned(p->plane[s].p, p->plane[s].pitch, 0, G::VX, sizeof(T)))
@@ -427,8 +433,8 @@ template <typename T> static int fused_kind_t(const gcmf_plan* p) {
         return FK_FLUX;
     }
     if (p->desc.op == GCMF_OP_REGULAR5) {
-        const int core = fl & ~GCMF_FLAG_AREA;  // prepare / finalize happen outside the fused mid steps
-        if (core == GCMF_FLAG_WRAP_Y) return FK_REG5;
+        const int core = base & ~GCMF_FLAG_AREA;  // prepare / finalize happen outside the recurrence arithmetic
+        if (core == GCMF_FLAG_WRAP_Y && !(fl & tripolar)) return FK_REG5;
         if (core == (GCMF_FLAG_WRAP_Y | GCMF_FLAG_MASK | GCMF_FLAG_NAN2NUM) && p->plane[0].p && p->plane[0].nb == 1)
             return FK_REG5;
     }

@@ -165,8 +165,30 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
         return x;                                                  // kernels.py:113-121: NaNs spread
     }
 
-    // Stage tile row r of a (2-D slice of a) global array: <= 2 bulk copies (split at the x wrap).
-    GCMF_HD void copy_row(T* dst_tile, const T* src_slice, int64_t pitch, int r, uint64_t* mb) const {
+    // ---- tripolar grids (FL_FOLD_N | FL_CUT_S; kernels.py:33-40) -------------------------------------------
+    // Tile rows above the top of the grid are VIRTUAL: row ny-1+r is the mirror image of row ny-r with the
+    // columns reversed, (ny-1+r, i) == (ny-r, nx-1-i).  A virtual cell is the real cell seen upside down: its
+    // east face is the real cell's west face and its north face the real cell's south face, so the halo above
+    // the fold evolves exactly like the real cells it mirrors.  Virtual rows cannot be bulk-copied (reversed):
+    // the issuing thread gathers them element by element (only the top row of tiles pays for this).
+    GCMF_HD bool fold() const { return (P.g.flags & FL_FOLD_N) != 0; }
+    GCMF_HD bool virtual_row(int r) const { return fold() && gy0 + r >= P.g.ny; }
+    GCMF_HD bool below_cut(int r) const { return (P.g.flags & FL_CUT_S) && gy0 + r < 0; }
+    GCMF_HD int image_row(int r) const { return 2 * P.g.ny - 1 - (gy0 + r); }          // real row of a virtual tile row
+    GCMF_HD int image_col(int c) const { return P.g.nx - 1 - wrap_index(gx0 + c, P.g.nx); }  // real column
+
+    // bytes of row r that arrive through bulk copies (the mbarrier's expected transaction count)
+    GCMF_HD unsigned row_tx_bytes(int r) const { return virtual_row(r) ? 0u : (unsigned)(G::TW * sizeof(T)); }
+
+    // Stage tile row r of a (2-D slice of a) global array: <= 2 bulk copies (split at the x wrap), or a
+    // reversed gather for a virtual row.  dj / di: index shift applied to the image cell (coefficient faces).
+    GCMF_HD void copy_row(T* dst_tile, const T* src_slice, int64_t pitch, int r, uint64_t* mb, int dj = 0,
+                          int di = 0) const {
+        if (virtual_row(r)) {
+            const T* row = src_slice + (int64_t)(image_row(r) + dj) * pitch;
+            for (int c = 0; c < G::TW; ++c) dst_tile[r * G::TW + c] = row[wrap_index(image_col(c) + di, P.g.nx)];
+            return;
+        }
         const int gy = wrap_index(gy0 + r, P.g.ny);
         const int gx = wrap_index(gx0, P.g.nx);
         const T* row = src_slice + (int64_t)gy * pitch;
@@ -174,12 +196,25 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
         bulk_copy_g2s(dst_tile + r * G::TW, row + gx, (unsigned)(n1 * sizeof(T)), mb);
         if (n1 < G::TW) bulk_copy_g2s(dst_tile + r * G::TW + n1, row, (unsigned)((G::TW - n1) * sizeof(T)), mb);
     }
-    // phase: thread r < TH issues the coefficient rows (FLUX)
+    // phase: thread r < TH stages the coefficient rows (FLUX).  Returns the bulk bytes it issued.
+    GCMF_HD unsigned coef_tx_bytes(int r) const {
+        return virtual_row(r) ? 0u : (below_cut(r) ? 2u : 3u) * (unsigned)(G::TW * sizeof(T));
+    }
     GCMF_HD void issue_coef_row(int r, uint64_t* mb) const {
-        for (int s = 0; s < 3; ++s)
-            copy_row(tileC(s), reinterpret_cast<const T*>(P.plane[s].p), P.plane[s].pitch, r, mb);
+        const T* ce = reinterpret_cast<const T*>(P.plane[0].p);
+        const T* cn = reinterpret_cast<const T*>(P.plane[1].p);
+        const T* ra = reinterpret_cast<const T*>(P.plane[2].p);
+        // virtual cell: east face = image's west face (di = -1), north face = image's south face (dj = -1)
+        copy_row(tileC(0), ce, P.plane[0].pitch, r, mb, 0, -1);
+        if (below_cut(r)) {  // no flux across the southern edge of row 0 (and nothing below it matters)
+            for (int c = 0; c < G::TW; ++c) tileC(1)[r * G::TW + c] = T(0);
+        } else {
+            copy_row(tileC(1), cn, P.plane[1].pitch, r, mb, -1, 0);
+        }
+        copy_row(tileC(2), ra, P.plane[2].pitch, r, mb);
     }
     // phase: thread r < TH issues row r of T1(level) -> X and T2(level) -> Y
+    GCMF_HD unsigned state_tx_bytes(int r) const { return (is_first() ? 1u : 2u) * row_tx_bytes(r); }
     GCMF_HD void issue_state_row(int r, int64_t level, uint64_t* mb) const {
         copy_row(tileX(), P.t1_in.p + level * P.t1_in.bstride, P.t1_in.pitch, r, mb);
         if (!is_first()) copy_row(tileY(), P.t2_in.p + level * P.t2_in.bstride, P.t2_in.pitch, r, mb);
@@ -201,16 +236,24 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
         const int64_t pitch = P.plane[0].pitch;
         uint32_t mb = 0;
         uint64_t wf = 0;
+        const int ny = P.g.ny, nx = P.g.nx;
         for (int q = 0; q < G::R; ++q) {
-            const int gy = wrap_index(gy0 + ty * G::R + q, P.g.ny);
-            const int gyn = gy + 1 == P.g.ny ? 0 : gy + 1, gys = gy == 0 ? P.g.ny - 1 : gy - 1;
+            const int r = ty * G::R + q;
+            const bool virt = virtual_row(r);
+            const int gy = virt ? image_row(r) : wrap_index(gy0 + r, ny);
             for (int v = 0; v < G::VX; ++v) {
-                const int gx = wrap_index(gx0 + tx * G::VX + v, P.g.nx);
-                const int gxe = gx + 1 == P.g.nx ? 0 : gx + 1, gxw = gx == 0 ? P.g.nx - 1 : gx - 1;
+                const int c = tx * G::VX + v;
+                const int gx = virt ? image_col(c) : wrap_index(gx0 + c, nx);
+                const int gxe = gx + 1 == nx ? 0 : gx + 1, gxw = gx == 0 ? nx - 1 : gx - 1;
                 const int idx = q * G::VX + v;
                 if (m[(int64_t)gy * pitch + gx]) mb |= 1u << idx;
+                // north neighbour of the top row is its mirror image across the fold (kernels.py:461-467)
+                const bool top = fold() && gy == ny - 1;
+                const int gyn = top ? ny - 1 : (gy + 1 == ny ? 0 : gy + 1);
+                const int gxn = top ? nx - 1 - gx : gx;
+                const int gys = gy == 0 ? ny - 1 : gy - 1;  // row 0 of a tripolar grid is land: inert
                 const uint64_t cnt = (m[(int64_t)gy * pitch + gxe] != 0) + (m[(int64_t)gy * pitch + gxw] != 0) +
-                                     (m[(int64_t)gyn * pitch + gx] != 0) + (m[(int64_t)gys * pitch + gx] != 0);
+                                     (m[(int64_t)gyn * pitch + gxn] != 0) + (m[(int64_t)gys * pitch + gx] != 0);
                 wf |= cnt << (4 * idx);
             }
         }
@@ -417,8 +460,6 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
     if (l0 >= l1) return;
     FusedTile<T, KIND, EDGE> tl(P, tile, smem);
     FusedThread<T> st;
-    const bool first = EDGE && P.first;
-    constexpr unsigned ROW_BYTES = G::TW * sizeof(T);
     if (tid == 0) {
         mbar_init(&mb[0], G::TH);
         mbar_init(&mb[1], G::TH);
@@ -429,11 +470,11 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
     __syncthreads();
     if (tid < G::TH) {
         if (KIND == FK_FLUX) {
-            mbar_expect_tx(&mb[0], 3 * ROW_BYTES);
-            tl.issue_coef_row(tid, &mb[0]);
+            tl.issue_coef_row(tid, &mb[0]);  // generic writes (virtual / cut rows) precede the releasing arrive
+            mbar_expect_tx(&mb[0], tl.coef_tx_bytes(tid));
         }
-        mbar_expect_tx(&mb[1], (first ? 1 : 2) * ROW_BYTES);
         tl.issue_state_row(tid, l0, &mb[1]);
+        mbar_expect_tx(&mb[1], tl.state_tx_bytes(tid));
     }
     tl.load_mask(tid, st);
     // FLUX steps are long enough for neighbour-only synchronisation to pay; the light REGULAR5 steps keep
@@ -449,8 +490,8 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
         __syncthreads();  // S0 complete; landing tiles consumed
         if (l + 1 < l1 && tid < G::TH) {  // next level's tiles fly during the k steps
             fence_proxy_async();
-            mbar_expect_tx(&mb[1], (first ? 1 : 2) * ROW_BYTES);
             tl.issue_state_row(tid, l + 1, &mb[1]);
+            mbar_expect_tx(&mb[1], tl.state_tx_bytes(tid));
         }
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {
@@ -503,8 +544,8 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
         old = __shfl_sync(0xffffffffu, old, 0);
         if (old == (uint32_t)NWARPS * (uint32_t)(it + 1) - 1u && l + 1 < l1) {
             fence_proxy_async();
-            mbar_expect_tx(&mb[1], (first ? 1 : 2) * ROW_BYTES);
             tl.issue_state_row(lane, l + 1, &mb[1]);
+            mbar_expect_tx(&mb[1], tl.state_tx_bytes(lane));
         }
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {

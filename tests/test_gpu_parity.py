@@ -266,6 +266,35 @@ def test_fused_steps_equal_one_step_kernels(g, dtype, shape):
     assert rel_l2(fused, ref) < (TOL64 if dtype == np.float64 else TOL32)
 
 
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (150, 380)), (np.float32, (96, 520))])
+@pytest.mark.parametrize("g", ["TRIPOLAR_POP_WITH_LAND", "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED"])
+def test_fused_tripolar_fold(g, dtype, shape):
+    """Fused tiles across the tripolar fold evolve mirrored halo rows: equal to the one-step kernels up to the
+    order in which mirrored cells sum their fluxes."""
+    from gcm_filters_b200 import engine
+    (f,), gv = fixtures.fixture(g, shape)
+    fb = np.stack([f, f * f, 1.0 - f]).astype(dtype)
+    fb[:, gv["wet_mask"] == 0] = np.nan
+    gvt = {k: v.astype(dtype) for k, v in gv.items()}
+    flt = make_filter(g, gvt, filter_scale=10.0, dx_min=1.0)
+    lib = _cabi.get_library()
+    try:
+        engine.set_steps_per_block(0)
+        n0 = lib.launch_count()
+        fused = flt.apply(fb, None)
+        n_fused = lib.launch_count() - n0
+        engine.set_steps_per_block(1)
+        plain = flt.apply(fb, None)
+    finally:
+        engine.set_steps_per_block(0)
+    assert n_fused == -(-flt.n_steps // 4) + (1 if "AREA" in g else 0)
+    assert np.array_equal(np.isnan(fused), np.isnan(plain))
+    assert rel_l2(fused, plain) < (1e-14 if dtype == np.float64 else 1e-6)
+    ref = np_oracle.apply_filter(g, gv, (fb.astype(np.float64),), filter_scale=10.0, dx_min=1.0)
+    assert rel_l2(fused, ref) < (TOL64 if dtype == np.float64 else TOL32)
+    assert rel_l2(fused[..., -8:, :], ref[..., -8:, :]) < (TOL64 if dtype == np.float64 else TOL32)
+
+
 def test_c_abi_error_reporting():
     lib = _cabi.get_library()
     with pytest.raises(_cabi.GcmfError, match="unknown op"):

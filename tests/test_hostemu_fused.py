@@ -70,14 +70,38 @@ def test_fused_f32():
     assert rel_l2(a, ref) < 1e-5
 
 
-def test_fused_not_offered_for_folded_or_small_grids():
-    (f,), gv = fixtures.fixture("TRIPOLAR_POP_WITH_LAND", (64, 200))
-    lap = ALL_KERNELS[GridType.TRIPOLAR_POP_WITH_LAND](**gv)
-    assert EmuPlan(lap, np.float64, 64, 200).lib.fused_max_steps(EmuPlan(lap, np.float64, 64, 200).h) == 0
+def test_fused_not_offered_for_small_grids():
     (f,), gv = fixtures.fixture("IRREGULAR_WITH_LAND", (30, 100))
     lap = ALL_KERNELS[GridType.IRREGULAR_WITH_LAND](**gv)
     pl = EmuPlan(lap, np.float64, 30, 100)
     assert pl.lib.fused_max_steps(pl.h) == 0
+
+
+@pytest.mark.parametrize("g", ["TRIPOLAR_POP_WITH_LAND", "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED"])
+@pytest.mark.parametrize("dtype,shape,n_steps", [(np.float64, (70, 250), 11), (np.float64, (33, 128), 6),
+                                                  (np.float32, (50, 300), 9)])
+def test_fused_tripolar_fold(g, dtype, shape, n_steps):
+    """Tiles that reach across the tripolar fold evolve virtual (mirrored) halo rows."""
+    (f,), gv = fixtures.fixture(g, shape)
+    rng = np.random.default_rng(4)
+    fb = np.stack([f + 0.1 * rng.standard_normal(shape), f * f])
+    fb[:, gv["wet_mask"] == 0] = np.nan
+    lap = ALL_KERNELS[GridType[g]](**gv)
+    spec = _compute_filter_spec(8.0, 1.0, FilterShape.GAUSSIAN, np.pi, 2, n_steps)
+    c = _shift_scale(spec, lap)
+    fused = EmuPlan(lap, dtype, *shape)
+    assert fused.lib.fused_max_steps(fused.h) == 4
+    (a,) = fused.filter((fb.astype(dtype),), spec.p, c)
+    plain = EmuPlan(lap, dtype, *shape)
+    emu_set_steps_per_block(plain, 1)
+    (b,) = plain.filter((fb.astype(dtype),), spec.p, c)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    # mirrored cells sum their E/W and N/S fluxes in the opposite order: equal to rounding, not bit for bit
+    assert rel_l2(a, b) < (1e-14 if dtype == np.float64 else 1e-6)
+    ref = np_oracle.run_recurrence(np_oracle.make_operator(g, gv), np_oracle.FilterSpec(*spec), (fb,))
+    assert rel_l2(a, ref) < (1e-12 if dtype == np.float64 else 1e-5)
+    top = rel_l2(a[..., -6:, :], ref[..., -6:, :])  # the rows next to the fold
+    assert top < (1e-12 if dtype == np.float64 else 1e-5)
 
 
 @pytest.mark.parametrize("g", ["REGULAR", "REGULAR_WITH_LAND", "REGULAR_WITH_LAND_AREA_WEIGHTED", "REGULAR_AREA_WEIGHTED"])
