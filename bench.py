@@ -380,6 +380,87 @@ def gpu_arm(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------ banded arm
+def banded_arm(args):
+    """One 2-D slice split into latitude bands, one band per GPU, ghost rows exchanged by NCCL point-to-point
+    after every Chebyshev step (BASELINE config 5).  Strong scaling: the total work is fixed."""
+    import torch
+    import torch.distributed as dist
+
+    from gcm_filters_b200 import Filter, FilterShape, GridType, _cabi
+    from gcm_filters_b200.scheduler import BandedFilter
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = build_workload(args.workload, args.nb)
+    fa = dict(cfg["filter_args"])
+    fa["filter_shape"] = FilterShape[fa["filter_shape"]]
+    flt = Filter(grid_type=GridType[cfg["grid_type"]], grid_vars=cfg["grid_vars"], **fa)
+    n_steps = int(flt.n_steps)
+    bf = BandedFilter(flt, rank, world)
+    st = bf.stage(*cfg["fields"])
+    f0 = cfg["fields"][0]
+    ny, nx = f0.shape[-2:]
+    nb = st["nb"]
+    w = f0.dtype.itemsize
+    lib = _cabi.get_library()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        bf.run(st)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream(dev)
+    e0.record(stream)
+    for _ in range(args.steps):
+        bf.run(st)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.launch_count() - n0
+    if world > 1:
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0].item()), int(t[1].item())
+        dist.barrier()
+        dist.destroy_process_group()
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return
+    units = nb * ny * nx * n_steps
+    value = units * args.steps / (ms * 1e-3)
+    ncomp = len(cfg["fields"])
+    b_alg = 5 * w * ncomp + c_bytes_per_point(cfg["grid_type"], w) / nb
+    peak, peak_src = measured_hbm_peak()
+    achieved = b_alg * value / 1e9 / world  # per GPU
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if w == 8 else "f32", "data": "synthetic (numpy PCG64, SURVEY 8(d))",
+        "config": dict(workload_descr(cfg, n_steps),
+                       sharding=f"{world} latitude band(s), 1 ghost row per side, NCCL send/recv per Chebyshev step"),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "step_kernel (one Chebyshev step per launch) + halo exchange, per GPU",
+                     "algorithmic_bytes_per_pt_step": b_alg, "peak_source": peak_src},
+        "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def reference_arm(args):
     """The reference is pure Python/numpy and cannot travel to the GPU box; its CPU implementation of
@@ -425,9 +506,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-per-block", type=int, default=0, help="0 auto, 1 = one-step kernels only")
+    ap.add_argument("--banded", action="store_true",
+                    help="latitude-band domain decomposition with NCCL halo exchange (strong scaling; cfg5)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.banded:
+        banded_arm(args)
     else:
         gpu_arm(args)
 

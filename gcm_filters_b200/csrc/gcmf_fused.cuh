@@ -184,17 +184,24 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     // reversed gather for a virtual row.  dj / di: index shift applied to the image cell (coefficient faces).
     GCMF_HD void copy_row(T* dst_tile, const T* src_slice, int64_t pitch, int r, uint64_t* mb, int dj = 0,
                           int di = 0) const {
-        if (virtual_row(r)) {
-            const T* row = src_slice + (int64_t)(image_row(r) + dj) * pitch;
-            for (int c = 0; c < G::TW; ++c) dst_tile[r * G::TW + c] = row[wrap_index(image_col(c) + di, P.g.nx)];
-            return;
-        }
+        (void)dj; (void)di;
+        if (virtual_row(r)) return;  // gathered cooperatively by gather_virtual()
         const int gy = wrap_index(gy0 + r, P.g.ny);
         const int gx = wrap_index(gx0, P.g.nx);
         const T* row = src_slice + (int64_t)gy * pitch;
         const int n1 = (P.g.nx - gx) < G::TW ? (P.g.nx - gx) : G::TW;
         bulk_copy_g2s(dst_tile + r * G::TW, row + gx, (unsigned)(n1 * sizeof(T)), mb);
         if (n1 < G::TW) bulk_copy_g2s(dst_tile + r * G::TW + n1, row, (unsigned)((G::TW - n1) * sizeof(T)), mb);
+    }
+    // Virtual rows of one tile, gathered by the 32 issuing lanes together (lane strides over the columns).
+    GCMF_HD void gather_virtual(int lane, T* dst_tile, const T* src_slice, int64_t pitch, int dj = 0, int di = 0) const {
+        if (!fold()) return;
+        int r0 = P.g.ny - gy0;  // first virtual tile row
+        if (r0 < 0) r0 = 0;
+        for (int r = r0; r < G::TH; ++r) {
+            const T* row = src_slice + (int64_t)(image_row(r) + dj) * pitch;
+            for (int c = lane; c < G::TW; c += 32) dst_tile[r * G::TW + c] = row[wrap_index(image_col(c) + di, P.g.nx)];
+        }
     }
     // phase: thread r < TH stages the coefficient rows (FLUX).  Returns the bulk bytes it issued.
     GCMF_HD unsigned coef_tx_bytes(int r) const {
@@ -205,6 +212,9 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
         const T* cn = reinterpret_cast<const T*>(P.plane[1].p);
         const T* ra = reinterpret_cast<const T*>(P.plane[2].p);
         // virtual cell: east face = image's west face (di = -1), north face = image's south face (dj = -1)
+        gather_virtual(r, tileC(0), ce, P.plane[0].pitch, 0, -1);
+        gather_virtual(r, tileC(1), cn, P.plane[1].pitch, -1, 0);
+        gather_virtual(r, tileC(2), ra, P.plane[2].pitch);
         copy_row(tileC(0), ce, P.plane[0].pitch, r, mb, 0, -1);
         if (below_cut(r)) {  // no flux across the southern edge of row 0 (and nothing below it matters)
             for (int c = 0; c < G::TW; ++c) tileC(1)[r * G::TW + c] = T(0);
@@ -216,6 +226,8 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     // phase: thread r < TH issues row r of T1(level) -> X and T2(level) -> Y
     GCMF_HD unsigned state_tx_bytes(int r) const { return (is_first() ? 1u : 2u) * row_tx_bytes(r); }
     GCMF_HD void issue_state_row(int r, int64_t level, uint64_t* mb) const {
+        gather_virtual(r, tileX(), P.t1_in.p + level * P.t1_in.bstride, P.t1_in.pitch);
+        if (!is_first()) gather_virtual(r, tileY(), P.t2_in.p + level * P.t2_in.bstride, P.t2_in.pitch);
         copy_row(tileX(), P.t1_in.p + level * P.t1_in.bstride, P.t1_in.pitch, r, mb);
         if (!is_first()) copy_row(tileY(), P.t2_in.p + level * P.t2_in.bstride, P.t2_in.pitch, r, mb);
     }

@@ -163,10 +163,9 @@ class BandedFilter:
             t[..., 0, :] = gs
 
     # ---- the filter on this rank's band -----------------------------------------------------------
-    def apply(self, *fields):
-        """``fields``: the GLOBAL component arrays (numpy, shape (..., ny, nx)); every rank passes the same
-        arrays and keeps only its band (+ ghost rows).  Returns this rank's rows [j0, j1) of the filtered
-        component(s) as numpy arrays, and (j0, j1)."""
+    def stage(self, *fields):
+        """Move this rank's band of the GLOBAL component arrays (numpy, shape (..., ny, nx)) to the device.
+        Returns the state :meth:`run` works on."""
         import torch
 
         lap = self.lap
@@ -179,18 +178,28 @@ class BandedFilter:
         nyl = j1 - j0
         nb = int(np.prod(f0.shape[:-2])) if f0.ndim > 2 else 1
         tdt = torch.float32 if np_dtype == np.float32 else torch.float64
-        ring = bool(lap._planes.flags & _cabi.FLAG_WRAP_Y) and not (lap._planes.flags & _cabi.FLAG_CUT_S)
-        n = int(self.spec.n_steps)
-        lib = self.lib
 
         def new():
             return torch.zeros((ncomp, nb, nyl + 2, nx), dtype=tdt, device=self.device)
 
-        X, A, B = new(), new(), new()
-        bar = torch.empty((ncomp, nb, nyl, nx), dtype=tdt, device=self.device)
+        X0 = new()
         for k, f in enumerate(fields):
             band = np.ascontiguousarray(np.asarray(f).reshape((nb, ny, nx))[:, j0:j1])
-            X[k, :, 1:nyl + 1] = torch.as_tensor(band).to(device=self.device, dtype=tdt)
+            X0[k, :, 1:nyl + 1] = torch.as_tensor(band).to(device=self.device, dtype=tdt)
+        return dict(h=h, flags=flags, j0=j0, j1=j1, nyl=nyl, nb=nb, nx=nx, ncomp=ncomp, X0=X0, X=new(), A=new(), B=new(),
+                    bar=torch.empty((ncomp, nb, nyl, nx), dtype=tdt, device=self.device), batch_shape=f0.shape[:-2])
+
+    def run(self, st):
+        """All n_steps Chebyshev steps on the device-resident band, one ghost-row exchange per step.
+        Nothing but kernel launches, small pack/unpack copies and NCCL point-to-point calls."""
+        import torch
+
+        lap, lib = self.lap, self.lib
+        h, flags, nyl, nb, nx, ncomp = st["h"], st["flags"], st["nyl"], st["nb"], st["nx"], st["ncomp"]
+        ring = bool(lap._planes.flags & _cabi.FLAG_WRAP_Y) and not (lap._planes.flags & _cabi.FLAG_CUT_S)
+        n = int(self.spec.n_steps)
+        X, A, B, bar = st["X"], st["A"], st["B"], st["bar"]
+        X.copy_(st["X0"])
         es = X.element_size()
 
         def inner(t):  # gcmf_field specs addressing the owned rows (row 1 of the ghosted array)
@@ -213,7 +222,18 @@ class BandedFilter:
             if i < n:
                 self._exchange(D, ring)
             T2, T1 = T1, D
+        return bar
+
+    def apply(self, *fields):
+        """``fields``: the GLOBAL component arrays (numpy, shape (..., ny, nx)); every rank passes the same
+        arrays and keeps only its band (+ ghost rows).  Returns this rank's rows [j0, j1) of the filtered
+        component(s) as numpy arrays, and (j0, j1)."""
+        import torch
+
+        st = self.stage(*fields)
+        bar = self.run(st)
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
-        outs = tuple(bar[k].reshape(f0.shape[:-2] + (nyl, nx)).cpu().numpy() for k in range(ncomp))
-        return outs, (j0, j1)
+        outs = tuple(bar[k].reshape(tuple(st["batch_shape"]) + (st["nyl"], st["nx"])).cpu().numpy()
+                     for k in range(st["ncomp"]))
+        return outs, (st["j0"], st["j1"])
