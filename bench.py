@@ -377,7 +377,7 @@ def gpu_arm(args):
                 "steps": e2e_steps, "api": "Filter.apply(pinned host tensor, out=pinned host tensor)"},
         "gpu_launches": total_launches, "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ banded arm
@@ -458,7 +458,7 @@ def banded_arm(args):
                      "algorithmic_bytes_per_pt_step": b_alg, "peak_source": peak_src},
         "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -492,10 +492,43 @@ def reference_arm(args):
         "cpu_baseline": res,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+class _CleanStdout:
+    """Everything written to fd 1 while the benchmark runs (NCCL prints its version there, libraries may
+    chatter) is diverted to stderr; the ONE JSON line goes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        os.write(self.real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
+_OUT = None
+
+
+def emit(line):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text)
 
 
 def main():
+    global _OUT
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -509,12 +542,17 @@ def main():
     ap.add_argument("--banded", action="store_true",
                     help="latitude-band domain decomposition with NCCL halo exchange (strong scaling; cfg5)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        reference_arm(args)
-    elif args.banded:
-        banded_arm(args)
-    else:
-        gpu_arm(args)
+    with _CleanStdout() as out:
+        _OUT = out
+        try:
+            if args.impl == "reference":
+                reference_arm(args)
+            elif args.banded:
+                banded_arm(args)
+            else:
+                gpu_arm(args)
+        finally:
+            _OUT = None
 
 
 if __name__ == "__main__":

@@ -196,6 +196,30 @@ __global__ void __launch_bounds__(BX* BY, GCMF_STEP_MINBLOCKS) step_kernel(const
     if (i0 < P.g.nx && j < P.g.ny) step_body<T, VX, OP, MODE>(P, b, j, i0);
 }
 
+// VECTOR_C: stresses once per point into shared memory, then the divergence (see CgridTile)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(CgridTile<T>::NTHREADS) cgrid_kernel(const __grid_constant__ StepParams<T> P, unsigned nxb) {
+    using C = CgridTile<T>;
+    __shared__ T sm[C::SMEM_ELEMS];
+    unsigned bid = blockIdx.x;
+    const unsigned xb = bid % nxb;
+    bid /= nxb;
+    const unsigned nbu = (unsigned)P.nb;
+    const int b = (int)(bid % nbu);
+    const int yb = (int)(bid / nbu);
+    const int j0 = yb * C::TY, i0 = (int)xb * C::TX;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < C::SW * C::SH; e += C::NTHREADS) C::stress(P, b, j0, i0, e, sm);
+    __syncthreads();
+    const int ty = tid / C::TX, tx = tid % C::TX;
+    const int j = j0 + ty, i = i0 + tx;
+    if (j < P.g.ny && i < P.g.nx) {
+        T lap[2][1], x[2][1];
+        C::divergence(P, b, j, i, ty, tx, sm, lap, x);
+        step_tail<T, 1, 2, false, MODE>(P, b, j, i, lap, x);
+    }
+}
+
 template <typename T>
 __global__ void prepare_kernel(const T* in, int64_t in_pitch, int64_t in_bs, T* out, int64_t out_pitch, int64_t out_bs,
                                PlaneRef area, int ny, int nx, int64_t nb) {
@@ -232,6 +256,50 @@ static int launch_step(const StepParams<T>& P, cudaStream_t st) {
 #endif
 }
 
+template <typename T, int MODE> static int launch_cgrid(const StepParams<T>& P, cudaStream_t st) {
+    using C = CgridTile<T>;
+    const int nxb = (P.g.nx + C::TX - 1) / C::TX;
+    const int nyb = (P.g.ny + C::TY - 1) / C::TY;
+#ifdef GCMF_HOSTEMU
+    (void)st;
+    std::vector<T> sm(C::SMEM_ELEMS);
+    for (int yb = 0; yb < nyb; ++yb)
+        for (int64_t b = 0; b < P.nb; ++b)
+            for (int xb = 0; xb < nxb; ++xb) {
+                const int j0 = yb * C::TY, i0 = xb * C::TX;
+                for (int e = 0; e < C::SW * C::SH; ++e) C::stress(P, (int)b, j0, i0, e, sm.data());
+                for (int tid = 0; tid < C::NTHREADS; ++tid) {
+                    const int ty = tid / C::TX, tx = tid % C::TX;
+                    const int j = j0 + ty, i = i0 + tx;
+                    if (j < P.g.ny && i < P.g.nx) {
+                        T lap[2][1], x[2][1];
+                        C::divergence(P, (int)b, j, i, ty, tx, sm.data(), lap, x);
+                        step_tail<T, 1, 2, false, MODE>(P, (int)b, j, i, lap, x);
+                    }
+                }
+            }
+    gcmf_count_launch(1);
+    return GCMF_OK;
+#else
+    const int64_t nblk = (int64_t)nxb * nyb * P.nb;
+    if (nblk > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "grid too large (%lld blocks)", (long long)nblk);
+    cgrid_kernel<T, MODE><<<(unsigned)nblk, C::NTHREADS, 0, st>>>(P, (unsigned)nxb);
+    gcmf_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCMF_OK;
+#endif
+}
+
+template <typename T> static int launch_cgrid_mode(const StepParams<T>& P, int mode, cudaStream_t st) {
+    switch (mode) {
+        case MODE_LAP: return launch_cgrid<T, MODE_LAP>(P, st);
+        case MODE_FIRST: return launch_cgrid<T, MODE_FIRST>(P, st);
+        case MODE_MID: return launch_cgrid<T, MODE_MID>(P, st);
+        case MODE_LAST: return launch_cgrid<T, MODE_LAST>(P, st);
+    }
+    return gcmf_set_error(GCMF_EINVAL, "bad mode %d", mode);
+}
+
 template <typename T, int VX, class OP>
 static int launch_mode(const StepParams<T>& P, int mode, cudaStream_t st) {
     switch (mode) {
@@ -255,7 +323,13 @@ static int launch_op(const gcmf_plan* pl, const StepParams<T>& P, int mode, cuda
             return launch_mode<T, VX, OpRegular5<T, VX, false>>(P, mode, st);
         case GCMF_OP_FLUX: return launch_mode<T, VX, OpFlux<T, VX>>(P, mode, st);
         case GCMF_OP_VECTOR_B: return launch_mode<T, VX, OpVectorB<T, VX>>(P, mode, st);
-        case GCMF_OP_VECTOR_C: return launch_mode<T, 1, OpVectorC<T, 1>>(P, mode, st);
+        case GCMF_OP_VECTOR_C: {
+            // tiled kernel needs every neighbour inside the array: at least 2 rows/columns; the point-wise
+            // OpVectorC kernel remains for degenerate grids (and as the test oracle of the tiled one)
+            static const bool pointwise = getenv("GCMF_CGRID_POINTWISE") != nullptr;
+            if (!pointwise && P.g.ny >= 2 && P.g.nx >= 2) return launch_cgrid_mode<T>(P, mode, st);
+            return launch_mode<T, 1, OpVectorC<T, 1>>(P, mode, st);
+        }
     }
     return gcmf_set_error(GCMF_EINVAL, "bad op");
 }

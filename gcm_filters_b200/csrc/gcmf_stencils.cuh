@@ -391,12 +391,21 @@ template <typename T, int VX> struct OpVectorC {
 // =====================================================================================
 // One Chebyshev step at VX points (filter.py:162-175, 185-206 scalar; :225-283 vector).
 // =====================================================================================
+template <typename T, int VX, int NC, bool FMA_SHIFT, int MODE>
+GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&lap)[NC][VX], const T (&x)[NC][VX]);
+
 template <typename T, int VX, class OP, int MODE>
 GCMF_HD void step_body(const StepParams<T>& P, int b, int j, int i0) {
     constexpr int NC = OP::NC;
     const Pt q = make_pt<VX>(P.g, b, j, i0);
     T lap[NC][VX], x[NC][VX];
     OP::apply(P, q, lap, x);
+    step_tail<T, VX, NC, OP::FMA_SHIFT, MODE>(P, b, j, i0, lap, x);
+}
+
+// The recurrence arithmetic that follows the Laplacian, shared by every one-step kernel.
+template <typename T, int VX, int NC, bool FMA_SHIFT, int MODE>
+GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&lap)[NC][VX], const T (&x)[NC][VX]) {
     const T c = (T)P.c;
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
@@ -410,7 +419,7 @@ GCMF_HD void step_body(const StepParams<T>& P, int b, int j, int i0) {
         T a[VX];
 #pragma unroll
         for (int v = 0; v < VX; ++v)  // shifted Laplacian, filter.py:171/173
-            a[v] = OP::FMA_SHIFT ? shifted_flux<T>(x[k][v], c, lap[k][v]) : (-x[k][v] - c * lap[k][v]);
+            a[v] = FMA_SHIFT ? shifted_flux<T>(x[k][v], c, lap[k][v]) : (-x[k][v] - c * lap[k][v]);
         T* barp = P.bar[k].p + (int64_t)b * P.bar[k].bstride + (int64_t)j * P.bar[k].pitch + i0;
         if (MODE == MODE_FIRST) {
             St<T, VX>::go(P.t0[k].p + (int64_t)b * P.t0[k].bstride + (int64_t)j * P.t0[k].pitch + i0, a);
@@ -439,6 +448,83 @@ GCMF_HD void step_body(const StepParams<T>& P, int b, int j, int i0) {
         }
     }
 }
+
+// =====================================================================================
+// VECTOR_C, tiled: the C-grid operator is two chained half-cell stages (stress tensor at T and q points, then
+// its divergence at u and v points; kernels.py:647-696).  A CTA first evaluates the four weighted stresses
+//   P1 = dyT^2*sxx, P2 = dxT^2*sxx (T points),  P3 = dxBu^2*sxy, P4 = dyBu^2*sxy (q points)
+// once per point of its tile (+1 row / column) into shared memory, then every thread differences them.
+// Same expressions, same order as OpVectorC::apply (bit-identical results), one third of the stress work.
+// =====================================================================================
+template <typename T> struct CgridTile {
+    static constexpr int TX = 32, TY = 8;               // output points per CTA
+    static constexpr int SW = TX + 1, SH = TY + 1;      // stress tiles: one extra column / row
+    static constexpr int NTHREADS = TX * TY;
+    static constexpr int SMEM_ELEMS = 4 * SW * SH;
+
+    // row / column index with the plan's boundary rule (periodic x; periodic y or ghost rows)
+    static GCMF_HD int wrap_row(const Geo& g, int j) {
+        if (!(g.flags & FL_WRAP_Y)) return j;
+        return j < 0 ? j + g.ny : (j >= g.ny ? j - g.ny : j);
+    }
+    static GCMF_HD int wrap_col(const Geo& g, int i) { return i < 0 ? i + g.nx : (i >= g.nx ? i - g.nx : i); }
+
+    // stage A: entry e of the stress tiles.  sxx-type entries sit at (j0 + r, i0 + cc), sxy-type at (j0-1+r, i0-1+cc).
+    static GCMF_HD void stress(const StepParams<T>& P, int b, int j0, int i0, int e, T* sm) {
+        const int r = e / SW, cc = e % SW;
+        const T* U = P.t1[0].p + (int64_t)b * P.t1[0].bstride;
+        const T* V = P.t1[1].p + (int64_t)b * P.t1[1].bstride;
+        const int64_t fp = P.t1[0].pitch, pp = P.plane[0].pitch;
+        const T* K[12];
+#pragma unroll
+        for (int s = 0; s < 12; ++s) K[s] = plane_base<T>(P.plane[s], b);
+        {   // T point (J, I): str_xx  (kernels.py:653-661)
+            const int J = wrap_row(P.g, j0 + r), I = wrap_col(P.g, i0 + cc);
+            const int Jm = wrap_row(P.g, j0 + r - 1), Im = wrap_col(P.g, i0 + cc - 1);
+            const T a_c = nan2num(U[(int64_t)J * fp + I]) * K[0][(int64_t)J * pp + I];
+            const T a_w = nan2num(U[(int64_t)J * fp + Im]) * K[0][(int64_t)J * pp + Im];
+            const T b_c = nan2num(V[(int64_t)J * fp + I]) * K[1][(int64_t)J * pp + I];
+            const T b_s = nan2num(V[(int64_t)Jm * fp + I]) * K[1][(int64_t)Jm * pp + I];
+            const T sxx = -(K[4][(int64_t)J * pp + I] * (a_c - a_w) - K[5][(int64_t)J * pp + I] * (b_c - b_s));
+            sm[0 * SW * SH + e] = K[8][(int64_t)J * pp + I] * sxx;   // dy2h * sxx
+            sm[1 * SW * SH + e] = K[9][(int64_t)J * pp + I] * sxx;   // dx2h * sxx
+        }
+        {   // q point (J, I): str_xy  (kernels.py:663-670)
+            const int J = wrap_row(P.g, j0 - 1 + r), I = wrap_col(P.g, i0 - 1 + cc);
+            const int Jp = wrap_row(P.g, j0 + r), Ip = wrap_col(P.g, i0 + cc);
+            const T c_c = nan2num(V[(int64_t)J * fp + I]) * K[2][(int64_t)J * pp + I];
+            const T c_e = nan2num(V[(int64_t)J * fp + Ip]) * K[2][(int64_t)J * pp + Ip];
+            const T e_c = nan2num(U[(int64_t)J * fp + I]) * K[3][(int64_t)J * pp + I];
+            const T e_n = nan2num(U[(int64_t)Jp * fp + I]) * K[3][(int64_t)Jp * pp + I];
+            const T sxy = -(K[6][(int64_t)J * pp + I] * (c_e - c_c) + K[7][(int64_t)J * pp + I] * (e_n - e_c));
+            sm[2 * SW * SH + e] = K[10][(int64_t)J * pp + I] * sxy;  // dx2q * sxy
+            sm[3 * SW * SH + e] = K[11][(int64_t)J * pp + I] * sxy;  // dy2q * sxy
+        }
+    }
+
+    // stage B: the divergence at output point (j0+ty, i0+tx)  (kernels.py:672-694)
+    static GCMF_HD void divergence(const StepParams<T>& P, int b, int j, int i, int ty, int tx, const T* sm,
+                                   T (&lap)[2][1], T (&x)[2][1]) {
+        const int64_t pp = P.plane[0].pitch;
+        const int64_t o = (int64_t)j * pp + i;
+        const T* P1 = sm;
+        const T* P2 = sm + SW * SH;
+        const T* P3 = sm + 2 * SW * SH;
+        const T* P4 = sm + 3 * SW * SH;
+        x[0][0] = P.t1[0].p[(int64_t)b * P.t1[0].bstride + (int64_t)j * P.t1[0].pitch + i];
+        x[1][0] = P.t1[1].p[(int64_t)b * P.t1[1].bstride + (int64_t)j * P.t1[1].pitch + i];
+        const T k0 = plane_base<T>(P.plane[0], b)[o], k1 = plane_base<T>(P.plane[1], b)[o];
+        const T k2 = plane_base<T>(P.plane[2], b)[o], k3 = plane_base<T>(P.plane[3], b)[o];
+        // T-point entries (r, cc) = (ty, tx); q-point entries are shifted by one: (j, i) -> (ty+1, tx+1)
+        const int t = ty * SW + tx, qd = (ty + 1) * SW + (tx + 1);
+        T uc = k0 * (P1[t] - P1[t + 1]);                 // 1/dyCu * (dy2h sxx - (dy2h sxx)[j,i+1])
+        uc = uc + k3 * (P3[qd - SW] - P3[qd]);           // + 1/dxCu * ((dx2q sxy)[j-1,i] - dx2q sxy)
+        lap[0][0] = uc * plane_base<T>(P.plane[12], b)[o];
+        T vc = k2 * (P4[qd - 1] - P4[qd]);               // 1/dyCv * ((dy2q sxy)[j,i-1] - dy2q sxy)
+        vc = vc - k1 * (P2[t] - P2[t + SW]);             // - 1/dxCv * (dx2h sxx - (dx2h sxx)[j+1,i])
+        lap[1][0] = vc * plane_base<T>(P.plane[13], b)[o];
+    }
+};
 
 // prepare: x = f * area (kernels.py:100-101)
 template <typename T>
