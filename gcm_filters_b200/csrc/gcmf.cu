@@ -197,8 +197,11 @@ __global__ void __launch_bounds__(BX* BY, GCMF_STEP_MINBLOCKS) step_kernel(const
 }
 
 // VECTOR_C: stresses once per point into shared memory, then the divergence (see CgridTile)
+#ifndef GCMF_CGRID_MINBLOCKS
+#define GCMF_CGRID_MINBLOCKS 6  // <= 40 registers: measured best on B200 (cfg5: 0.46 ms vs 0.72 ms per step at 92 registers)
+#endif
 template <typename T, int MODE>
-__global__ void __launch_bounds__(CgridTile<T>::NTHREADS) cgrid_kernel(const __grid_constant__ StepParams<T> P, unsigned nxb) {
+__global__ void __launch_bounds__(CgridTile<T>::NTHREADS, GCMF_CGRID_MINBLOCKS) cgrid_kernel(const __grid_constant__ StepParams<T> P, unsigned nxb) {
     using C = CgridTile<T>;
     __shared__ T sm[C::SMEM_ELEMS];
     unsigned bid = blockIdx.x;
