@@ -330,3 +330,26 @@ def test_pipelined_host_path_matches_monolithic():
     assert res is pin_out and np.array_equal(pin_out.numpy(), mono, equal_nan=True)
     ref = np_oracle.apply_filter("IRREGULAR_WITH_LAND", gv, (fb,), filter_scale=8.0, dx_min=1.0)
     assert rel_l2(piped, ref) < TOL64
+
+
+def test_fused_neighbour_sync_is_deterministic():
+    """The flux kernel replaces the CTA barrier by release/acquire progress flags between neighbouring warps
+    (compute-sanitizer racecheck only models barriers and cannot see them).  A missing dependency would show
+    up as run-to-run differences: 25 repetitions must agree bit for bit with each other and with the
+    barrier-free one-step kernels."""
+    import torch
+    from gcm_filters_b200 import engine
+    (f,), gv = fixtures.fixture("IRREGULAR_WITH_LAND", (480, 720))
+    rng = np.random.default_rng(9)
+    fb = f[None] * (1 + 0.2 * rng.standard_normal((6, 1, 1)))
+    fb[:, gv["wet_mask"] == 0] = np.nan
+    flt = make_filter("IRREGULAR_WITH_LAND", gv, filter_scale=16.0, dx_min=1.0)
+    t = torch.as_tensor(fb).cuda()
+    try:
+        engine.set_steps_per_block(1)
+        plain = flt.apply(t, None).clone()
+    finally:
+        engine.set_steps_per_block(0)
+    for rep in range(25):
+        out = flt.apply(t, None)
+        assert torch.equal(torch.nan_to_num(out, nan=-1.0), torch.nan_to_num(plain, nan=-1.0)), rep
