@@ -19,7 +19,7 @@ EXPORTS = [
     "gcmf_version", "gcmf_sm_arch", "gcmf_last_error", "gcmf_plan_create", "gcmf_plan_destroy",
     "gcmf_plan_set_plane", "gcmf_plan_set_filter", "gcmf_workspace_bytes", "gcmf_laplacian", "gcmf_filter",
     "gcmf_cheb_step", "gcmf_prepare", "gcmf_launch_count", "gcmf_fused_max_steps", "gcmf_plan_set_steps_per_block",
-    "gcmf_cheb_fused",
+    "gcmf_cheb_fused", "gcmf_cheb_step_halo", "gcmf_halo_push",
 ]
 
 
@@ -30,6 +30,14 @@ class PlanDesc(ctypes.Structure):
 
 class Field(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("pitch", ctypes.c_int64), ("bstride", ctypes.c_int64)]
+
+
+class Halo(ctypes.Structure):
+    _fields_ = [("north_ghost", ctypes.c_void_p * 2), ("south_ghost", ctypes.c_void_p * 2),
+                ("north_bstride", ctypes.c_int64), ("south_bstride", ctypes.c_int64),
+                ("wait_north", ctypes.c_void_p), ("wait_south", ctypes.c_void_p),
+                ("signal_north", ctypes.c_void_p), ("signal_south", ctypes.c_void_p),
+                ("wait_value", ctypes.c_uint32), ("signal_value", ctypes.c_uint32), ("counters", ctypes.c_void_p)]
 
 
 class GcmfError(RuntimeError):
@@ -68,6 +76,11 @@ class Library:
         lib.gcmf_plan_set_steps_per_block.restype = ctypes.c_int
         lib.gcmf_cheb_fused.argtypes = [vp, i64, i32, i32, fp, fp, fp, fp, fp, vp]
         lib.gcmf_cheb_fused.restype = ctypes.c_int
+        hp = ctypes.POINTER(Halo)
+        lib.gcmf_cheb_step_halo.argtypes = [vp, i64, i32, fp, fp, fp, fp, hp, vp]
+        lib.gcmf_cheb_step_halo.restype = ctypes.c_int
+        lib.gcmf_halo_push.argtypes = [vp, i64, fp, hp, vp]
+        lib.gcmf_halo_push.restype = ctypes.c_int
         for name in ("gcmf_plan_create", "gcmf_plan_destroy", "gcmf_plan_set_plane", "gcmf_plan_set_filter",
                      "gcmf_workspace_bytes", "gcmf_laplacian", "gcmf_prepare", "gcmf_filter", "gcmf_cheb_step"):
             getattr(lib, name).restype = ctypes.c_int
@@ -132,6 +145,13 @@ class Library:
     def cheb_fused(self, h, nb, step, k, t1, t2, t1o, t2o, bar, stream=0):
         self.check(self.lib.gcmf_cheb_fused(h, nb, step, k, self.fields(t1), self.fields(t2), self.fields(t1o),
                                             self.fields(t2o), self.fields(bar), ctypes.c_void_p(stream)))
+
+    def cheb_step_halo(self, h, nb, step, t1, t2, t0, bar, halo, stream=0):
+        self.check(self.lib.gcmf_cheb_step_halo(h, nb, step, self.fields(t1), self.fields(t2), self.fields(t0),
+                                                self.fields(bar), ctypes.byref(halo), ctypes.c_void_p(stream)))
+
+    def halo_push(self, h, nb, field, halo, stream=0):
+        self.check(self.lib.gcmf_halo_push(h, nb, self.fields(field), ctypes.byref(halo), ctypes.c_void_p(stream)))
 
     def launch_count(self):
         return int(self.lib.gcmf_launch_count())

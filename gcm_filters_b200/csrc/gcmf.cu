@@ -176,11 +176,56 @@ extern "C" int gcmf_workspace_bytes(const gcmf_plan* p, int64_t nb, size_t* byte
 // ------------------------------------------------------------------ kernels
 constexpr int BX = 32, BY = 8;
 
+// ---- halo flags (system scope: the neighbour GPU writes / reads them over NVLink) ----
+#ifndef GCMF_HOSTEMU
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// CTAs of the first / last row band: wait until the neighbour's rows have landed in my ghost rows
+template <typename T> __device__ __forceinline__ void halo_wait(const HaloRef<T>& h, bool bottom, bool top) {
+    if (!h.enabled || !(bottom || top)) return;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        unsigned spins = 0;
+        if (bottom && h.wait_s)
+            while ((int32_t)(ld_acquire_sys(h.wait_s) - h.wait_v) < 0)
+                if (++spins > (1u << 30)) asm volatile("trap;");
+        if (top && h.wait_n)
+            while ((int32_t)(ld_acquire_sys(h.wait_n) - h.wait_v) < 0)
+                if (++spins > (1u << 30)) asm volatile("trap;");
+    }
+    __syncthreads();
+}
+// ... and tell the neighbours once every border CTA of this launch has pushed its rows ("last block" pattern)
+template <typename T>
+__device__ __forceinline__ void halo_signal(const HaloRef<T>& h, bool bottom, bool top, unsigned n_border) {
+    if (!h.enabled || !(bottom || top)) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        if (top && h.sig_n && atomicAdd(&h.counters[0], 1u) == n_border - 1) {
+            h.counters[0] = 0;
+            __threadfence_system();
+            st_release_sys(h.sig_n, h.sig_v);
+        }
+        if (bottom && h.sig_s && atomicAdd(&h.counters[1], 1u) == n_border - 1) {
+            h.counters[1] = 0;
+            __threadfence_system();
+            st_release_sys(h.sig_s, h.sig_v);
+        }
+    }
+}
+#endif
+
 // 1-D grid; block id decodes as (x-block fastest, then batch, then row band): every batch slice
 // of a row band is swept before the next band, so the band's coefficient-plane rows are read
 // from HBM once and hit in L2 for the other nb-1 slices.
 #ifndef GCMF_HOSTEMU
-template <typename T, int VX, class OP, int MODE>
+template <typename T, int VX, class OP, int MODE, bool HALO>
 #ifndef GCMF_STEP_MINBLOCKS
 #define GCMF_STEP_MINBLOCKS 1
 #endif
@@ -193,14 +238,17 @@ __global__ void __launch_bounds__(BX* BY, GCMF_STEP_MINBLOCKS) step_kernel(const
     const int yb = (int)(bid / nbu);
     const int i0 = (int)(xb * BX + threadIdx.x) * VX;
     const int j = yb * BY + (int)threadIdx.y;
-    if (i0 < P.g.nx && j < P.g.ny) step_body<T, VX, OP, MODE>(P, b, j, i0);
+    const bool bottom = yb == 0, top = (yb + 1) * BY >= P.g.ny;
+    if (HALO) halo_wait<T>(P.halo, bottom, top);
+    if (i0 < P.g.nx && j < P.g.ny) step_body<T, VX, OP, MODE, HALO>(P, b, j, i0);
+    if (HALO) halo_signal<T>(P.halo, bottom, top, nxb * nbu);
 }
 
 // VECTOR_C: stresses once per point into shared memory, then the divergence (see CgridTile)
 #ifndef GCMF_CGRID_MINBLOCKS
 #define GCMF_CGRID_MINBLOCKS 6  // <= 40 registers: measured best on B200 (cfg5: 0.46 ms vs 0.72 ms per step at 92 registers)
 #endif
-template <typename T, int MODE>
+template <typename T, int MODE, bool HALO>
 __global__ void __launch_bounds__(CgridTile<T>::NTHREADS, GCMF_CGRID_MINBLOCKS) cgrid_kernel(const __grid_constant__ StepParams<T> P, unsigned nxb) {
     using C = CgridTile<T>;
     __shared__ T sm[C::SMEM_ELEMS];
@@ -212,6 +260,8 @@ __global__ void __launch_bounds__(CgridTile<T>::NTHREADS, GCMF_CGRID_MINBLOCKS) 
     const int yb = (int)(bid / nbu);
     const int j0 = yb * C::TY, i0 = (int)xb * C::TX;
     const int tid = threadIdx.x;
+    const bool bottom = yb == 0, top = (yb + 1) * C::TY >= P.g.ny;
+    if (HALO) halo_wait<T>(P.halo, bottom, top);
     for (int e = tid; e < C::SW * C::SH; e += C::NTHREADS) C::stress(P, b, j0, i0, e, sm);
     __syncthreads();
     const int ty = tid / C::TX, tx = tid % C::TX;
@@ -219,8 +269,27 @@ __global__ void __launch_bounds__(CgridTile<T>::NTHREADS, GCMF_CGRID_MINBLOCKS) 
     if (j < P.g.ny && i < P.g.nx) {
         T lap[2][1], x[2][1];
         C::divergence(P, b, j, i, ty, tx, sm, lap, x);
-        step_tail<T, 1, 2, false, MODE>(P, b, j, i, lap, x);
+        step_tail<T, 1, 2, false, MODE, HALO>(P, b, j, i, lap, x);
     }
+    if (HALO) halo_signal<T>(P.halo, bottom, top, nxb * nbu);
+}
+
+// Copy my first / last owned rows of a field into the neighbours' ghost rows and raise their flags (the
+// exchange of the prepared input before step 1).  One CTA column per x-block; grid (nxb, nb).
+template <typename T>
+__global__ void halo_push_kernel(FieldRef<const T> f0, FieldRef<const T> f1, int ncomp, int ny, int nx, HaloRef<T> h) {
+    halo_wait<T>(h, true, true);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i < nx) {
+        for (int k = 0; k < ncomp; ++k) {
+            const FieldRef<const T>& f = k ? f1 : f0;
+            const T* base = f.p + (int64_t)b * f.bstride;
+            if (h.north[k]) h.north[k][(int64_t)b * h.nbs + i] = base[(int64_t)(ny - 1) * f.pitch + i];
+            if (h.south[k]) h.south[k][(int64_t)b * h.sbs + i] = base[i];
+        }
+    }
+    halo_signal<T>(h, true, true, gridDim.x * gridDim.y);
 }
 
 template <typename T>
@@ -244,7 +313,10 @@ static int launch_step(const StepParams<T>& P, cudaStream_t st) {
     (void)st;
     for (int64_t b = 0; b < P.nb; ++b)
         for (int j = 0; j < P.g.ny; ++j)
-            for (int i0 = 0; i0 < P.g.nx; i0 += VX) step_body<T, VX, OP, MODE>(P, (int)b, j, i0);
+            for (int i0 = 0; i0 < P.g.nx; i0 += VX) {
+                if (P.halo.enabled) step_body<T, VX, OP, MODE, true>(P, (int)b, j, i0);
+                else step_body<T, VX, OP, MODE, false>(P, (int)b, j, i0);
+            }
     gcmf_count_launch(1);
     return GCMF_OK;
 #else
@@ -252,7 +324,8 @@ static int launch_step(const StepParams<T>& P, cudaStream_t st) {
     const int nyb = (P.g.ny + BY - 1) / BY;
     const int64_t nblk = (int64_t)nxb * nyb * P.nb;
     if (nblk > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "grid too large (%lld blocks)", (long long)nblk);
-    step_kernel<T, VX, OP, MODE><<<(unsigned)nblk, dim3(BX, BY), 0, st>>>(P, (unsigned)nxb);
+    if (P.halo.enabled) step_kernel<T, VX, OP, MODE, true><<<(unsigned)nblk, dim3(BX, BY), 0, st>>>(P, (unsigned)nxb);
+    else step_kernel<T, VX, OP, MODE, false><<<(unsigned)nblk, dim3(BX, BY), 0, st>>>(P, (unsigned)nxb);
     gcmf_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return GCMF_OK;
@@ -277,7 +350,8 @@ template <typename T, int MODE> static int launch_cgrid(const StepParams<T>& P, 
                     if (j < P.g.ny && i < P.g.nx) {
                         T lap[2][1], x[2][1];
                         C::divergence(P, (int)b, j, i, ty, tx, sm.data(), lap, x);
-                        step_tail<T, 1, 2, false, MODE>(P, (int)b, j, i, lap, x);
+                        if (P.halo.enabled) step_tail<T, 1, 2, false, MODE, true>(P, (int)b, j, i, lap, x);
+                        else step_tail<T, 1, 2, false, MODE, false>(P, (int)b, j, i, lap, x);
                     }
                 }
             }
@@ -286,7 +360,8 @@ template <typename T, int MODE> static int launch_cgrid(const StepParams<T>& P, 
 #else
     const int64_t nblk = (int64_t)nxb * nyb * P.nb;
     if (nblk > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "grid too large (%lld blocks)", (long long)nblk);
-    cgrid_kernel<T, MODE><<<(unsigned)nblk, C::NTHREADS, 0, st>>>(P, (unsigned)nxb);
+    if (P.halo.enabled) cgrid_kernel<T, MODE, true><<<(unsigned)nblk, C::NTHREADS, 0, st>>>(P, (unsigned)nxb);
+    else cgrid_kernel<T, MODE, false><<<(unsigned)nblk, C::NTHREADS, 0, st>>>(P, (unsigned)nxb);
     gcmf_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return GCMF_OK;
@@ -360,11 +435,34 @@ template <typename T> static bool can_vectorize(const gcmf_plan* pl, const StepP
     return true;
 }
 
+template <typename T> static HaloRef<T> make_halo(const gcmf_halo* h) {
+    HaloRef<T> r;
+    memset(&r, 0, sizeof r);
+    if (!h) return r;
+    for (int k = 0; k < 2; ++k) {
+        r.north[k] = (T*)h->north_ghost[k];
+        r.south[k] = (T*)h->south_ghost[k];
+    }
+    r.nbs = h->north_bstride;
+    r.sbs = h->south_bstride;
+    r.wait_n = h->wait_north;
+    r.wait_s = h->wait_south;
+    r.sig_n = h->signal_north;
+    r.sig_s = h->signal_south;
+    r.wait_v = h->wait_value;
+    r.sig_v = h->signal_value;
+    r.counters = h->counters;
+    r.enabled = 1;
+    return r;
+}
+
 template <typename T>
 static int run_step_t(const gcmf_plan* pl, int64_t nb, int mode, const gcmf_field* t1, const gcmf_field* t2,
-                      const gcmf_field* t0, const gcmf_field* bar, double p0, double p1, cudaStream_t st) {
+                      const gcmf_field* t0, const gcmf_field* bar, double p0, double p1, cudaStream_t st,
+                      const gcmf_halo* halo = nullptr) {
     StepParams<T> P;
     memset(&P, 0, sizeof P);
+    P.halo = make_halo<T>(halo);
     P.g.ny = pl->desc.ny;
     P.g.nx = pl->desc.nx;
     P.g.flags = pl->desc.flags;
@@ -379,14 +477,32 @@ static int run_step_t(const gcmf_plan* pl, int64_t nb, int mode, const gcmf_fiel
     P.p0 = p0;
     P.p1 = p1;
     P.nb = nb;
-    if (can_vectorize<T>(pl, P, mode)) return launch_op<T, VecWidth<T>::value>(pl, P, mode, st);
+    bool vec = can_vectorize<T>(pl, P, mode);
+    if (vec && halo) {  // the neighbours' ghost rows must take vector stores too
+        const int vx = VecWidth<T>::value;
+        for (int k = 0; k < pl->ncomp; ++k)
+            vec = vec && (uintptr_t)halo->north_ghost[k] % (vx * sizeof(T)) == 0 &&
+                  (uintptr_t)halo->south_ghost[k] % (vx * sizeof(T)) == 0;
+        vec = vec && halo->north_bstride % vx == 0 && halo->south_bstride % vx == 0;
+    }
+#ifdef GCMF_HOSTEMU
+    int rc = vec ? launch_op<T, VecWidth<T>::value>(pl, P, mode, st) : launch_op<T, 1>(pl, P, mode, st);
+    if (rc == GCMF_OK && halo) {  // the emulator has no concurrency: raise the flags after the "launch"
+        if (halo->signal_north) *halo->signal_north = halo->signal_value;
+        if (halo->signal_south) *halo->signal_south = halo->signal_value;
+    }
+    return rc;
+#else
+    if (vec) return launch_op<T, VecWidth<T>::value>(pl, P, mode, st);
     return launch_op<T, 1>(pl, P, mode, st);
+#endif
 }
 
 static int run_step(const gcmf_plan* pl, int64_t nb, int mode, const gcmf_field* t1, const gcmf_field* t2,
-                    const gcmf_field* t0, const gcmf_field* bar, double p0, double p1, cudaStream_t st) {
-    if (pl->desc.dtype == GCMF_F64) return run_step_t<double>(pl, nb, mode, t1, t2, t0, bar, p0, p1, st);
-    return run_step_t<float>(pl, nb, mode, t1, t2, t0, bar, p0, p1, st);
+                    const gcmf_field* t0, const gcmf_field* bar, double p0, double p1, cudaStream_t st,
+                    const gcmf_halo* halo = nullptr) {
+    if (pl->desc.dtype == GCMF_F64) return run_step_t<double>(pl, nb, mode, t1, t2, t0, bar, p0, p1, st, halo);
+    return run_step_t<float>(pl, nb, mode, t1, t2, t0, bar, p0, p1, st, halo);
 }
 
 static int check_fields(const gcmf_plan* p, const gcmf_field* f, const char* what) {
@@ -472,7 +588,52 @@ extern "C" int gcmf_prepare(gcmf_plan* p, int64_t nb, const gcmf_field* in, cons
 
 extern "C" int gcmf_cheb_step(gcmf_plan* p, int64_t nb, int32_t step, const gcmf_field* t1_in, const gcmf_field* t2,
                               const gcmf_field* t0_out, const gcmf_field* bar, void* stream) {
+    return gcmf_cheb_step_halo(p, nb, step, t1_in, t2, t0_out, bar, nullptr, stream);
+}
+
+template <typename T>
+static int run_halo_push_t(const gcmf_plan* p, int64_t nb, const gcmf_field* f, const gcmf_halo* halo, cudaStream_t st) {
+    HaloRef<T> h = make_halo<T>(halo);
+    const int ny = p->desc.ny, nx = p->desc.nx;
+#ifdef GCMF_HOSTEMU
+    (void)st;
+    for (int k = 0; k < p->ncomp; ++k)
+        for (int64_t b = 0; b < nb; ++b)
+            for (int i = 0; i < nx; ++i) {
+                const T* base = (const T*)f[k].ptr + b * f[k].bstride;
+                if (h.north[k]) h.north[k][b * h.nbs + i] = base[(int64_t)(ny - 1) * f[k].pitch + i];
+                if (h.south[k]) h.south[k][b * h.sbs + i] = base[i];
+            }
+    if (h.sig_n) *h.sig_n = h.sig_v;
+    if (h.sig_s) *h.sig_s = h.sig_v;
+    gcmf_count_launch(1);
+    return GCMF_OK;
+#else
+    FieldRef<const T> f0{(const T*)f[0].ptr, f[0].pitch, f[0].bstride};
+    FieldRef<const T> f1 = p->ncomp > 1 ? FieldRef<const T>{(const T*)f[1].ptr, f[1].pitch, f[1].bstride} : f0;
+    dim3 blk(256), grd((nx + 255) / 256, (unsigned)nb);
+    halo_push_kernel<T><<<grd, blk, 0, st>>>(f0, f1, p->ncomp, ny, nx, h);
+    gcmf_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCMF_OK;
+#endif
+}
+
+extern "C" int gcmf_halo_push(gcmf_plan* p, int64_t nb, const gcmf_field* field, const gcmf_halo* halo, void* stream) {
+    if (!p || nb < 1 || !halo) return gcmf_set_error(GCMF_EINVAL, "bad argument");
+    if (nb > 65535) return gcmf_set_error(GCMF_EINVAL, "halo push: nb too large");
+    if (p->desc.flags & GCMF_FLAG_WRAP_Y) return gcmf_set_error(GCMF_EINVAL, "halo exchange needs a band plan (no GCMF_FLAG_WRAP_Y)");
+    TRY(check_fields(p, field, "field"));
+    CUDA_TRY(cudaSetDevice(p->desc.device));
+    if (p->desc.dtype == GCMF_F64) return run_halo_push_t<double>(p, nb, field, halo, (cudaStream_t)stream);
+    return run_halo_push_t<float>(p, nb, field, halo, (cudaStream_t)stream);
+}
+
+extern "C" int gcmf_cheb_step_halo(gcmf_plan* p, int64_t nb, int32_t step, const gcmf_field* t1_in, const gcmf_field* t2,
+                                   const gcmf_field* t0_out, const gcmf_field* bar, const gcmf_halo* halo, void* stream) {
     if (!p || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
+    if (halo && (p->desc.flags & GCMF_FLAG_WRAP_Y))
+        return gcmf_set_error(GCMF_EINVAL, "halo exchange needs a band plan (no GCMF_FLAG_WRAP_Y)");
     if (p->n_steps < 2) return gcmf_set_error(GCMF_ESTATE, "gcmf_plan_set_filter has not been called");
     if (step < 1 || step > p->n_steps) return gcmf_set_error(GCMF_EINVAL, "step %d outside 1..%d", step, p->n_steps);
     TRY(check_planes(p));
@@ -487,7 +648,7 @@ extern "C" int gcmf_cheb_step(gcmf_plan* p, int64_t nb, int32_t step, const gcmf
     }
     CUDA_TRY(cudaSetDevice(p->desc.device));
     const double p0 = p->p[0], p1 = mode == MODE_FIRST ? p->p[1] : p->p[step];
-    return run_step(p, nb, mode, t1_in, t2, t0_out, bar, p0, p1, (cudaStream_t)stream);
+    return run_step(p, nb, mode, t1_in, t2, t0_out, bar, p0, p1, (cudaStream_t)stream, halo);
 }
 
 // ------------------------------------------------------------------ temporally blocked steps

@@ -80,6 +80,22 @@ struct Geo {
     int32_t flags;
 };
 
+// Ghost-row exchange of a latitude band through peer memory (NVLink): while a step kernel writes T_i it also
+// stores its first / last owned row straight into the neighbouring GPU's ghost row, then raises a flag in
+// the neighbour's memory; the next step on that GPU waits for the flag before it touches its ghost rows.
+template <typename T> struct HaloRef {
+    T* north[2];             // neighbour's ghost row that mirrors my row ny-1 (element b=0, i=0), per component
+    T* south[2];             // neighbour's ghost row that mirrors my row 0
+    int64_t nbs, sbs;        // batch strides of the neighbours' arrays
+    const uint32_t* wait_n;  // LOCAL flags raised by the neighbours: ghost rows of t1 are valid once >= wait_v
+    const uint32_t* wait_s;
+    uint32_t* sig_n;         // flags in the neighbours' memory, set to sig_v when my rows have landed there
+    uint32_t* sig_s;
+    uint32_t wait_v, sig_v;
+    uint32_t* counters;      // LOCAL [2]: border CTAs done (top, bottom); self-resetting
+    int32_t enabled;
+};
+
 // Everything one launch needs.  NC = number of field components (1 scalar, 2 vector).
 template <typename T> struct StepParams {
     Geo g;
@@ -91,6 +107,7 @@ template <typename T> struct StepParams {
     double c;                 // 2/s_max  or 2/(s_max dx_min^2)        (filter.py:168-173)
     double p0, p1;            // FIRST: p[0], p[1];  MID/LAST: p1 = p[i]
     int64_t nb;
+    HaloRef<T> halo;          // enabled only for band-decomposed plans driven through gcmf_cheb_step_halo
 };
 
 // Per-thread point context: rows/columns of the neighbours after wrap / fold handling.
@@ -164,6 +181,14 @@ template <> struct St<float, 4> {
     }
 };
 #endif
+
+// store the freshly computed row segment into the neighbours' ghost rows (peer memory)
+template <typename T, int VX>
+GCMF_HD void halo_push_row(const StepParams<T>& P, int k, int b, int j, int i0, const T (&v)[VX]) {
+    if (!P.halo.enabled) return;
+    if (j == P.g.ny - 1 && P.halo.north[k]) St<T, VX>::go(P.halo.north[k] + (int64_t)b * P.halo.nbs + i0, v);
+    if (j == 0 && P.halo.south[k]) St<T, VX>::go(P.halo.south[k] + (int64_t)b * P.halo.sbs + i0, v);
+}
 
 // 5-point neighbourhood of VX consecutive points of row j.
 template <typename S, int VX> struct Nb {
@@ -391,20 +416,21 @@ template <typename T, int VX> struct OpVectorC {
 // =====================================================================================
 // One Chebyshev step at VX points (filter.py:162-175, 185-206 scalar; :225-283 vector).
 // =====================================================================================
-template <typename T, int VX, int NC, bool FMA_SHIFT, int MODE>
+template <typename T, int VX, int NC, bool FMA_SHIFT, int MODE, bool HALO>
 GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&lap)[NC][VX], const T (&x)[NC][VX]);
 
-template <typename T, int VX, class OP, int MODE>
+template <typename T, int VX, class OP, int MODE, bool HALO = false>
 GCMF_HD void step_body(const StepParams<T>& P, int b, int j, int i0) {
     constexpr int NC = OP::NC;
     const Pt q = make_pt<VX>(P.g, b, j, i0);
     T lap[NC][VX], x[NC][VX];
     OP::apply(P, q, lap, x);
-    step_tail<T, VX, NC, OP::FMA_SHIFT, MODE>(P, b, j, i0, lap, x);
+    step_tail<T, VX, NC, OP::FMA_SHIFT, MODE, HALO>(P, b, j, i0, lap, x);
 }
 
 // The recurrence arithmetic that follows the Laplacian, shared by every one-step kernel.
-template <typename T, int VX, int NC, bool FMA_SHIFT, int MODE>
+// HALO: also store the new row into the neighbouring GPUs' ghost rows (band decomposition).
+template <typename T, int VX, int NC, bool FMA_SHIFT, int MODE, bool HALO>
 GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&lap)[NC][VX], const T (&x)[NC][VX]) {
     const T c = (T)P.c;
 #pragma unroll
@@ -423,6 +449,7 @@ GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&l
         T* barp = P.bar[k].p + (int64_t)b * P.bar[k].bstride + (int64_t)j * P.bar[k].pitch + i0;
         if (MODE == MODE_FIRST) {
             St<T, VX>::go(P.t0[k].p + (int64_t)b * P.t0[k].bstride + (int64_t)j * P.t0[k].pitch + i0, a);
+            if (HALO) halo_push_row<T, VX>(P, k, b, j, i0, a);
 #pragma unroll
             for (int v = 0; v < VX; ++v)  // filter.py:195
                 outv[v] = (T)(P.p0 * (double)x[k][v] + P.p1 * (double)a[v]);
@@ -438,6 +465,7 @@ GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&l
             }
             if (MODE == MODE_MID) {
                 St<T, VX>::go(P.t0[k].p + (int64_t)b * P.t0[k].bstride + (int64_t)j * P.t0[k].pitch + i0, t0);
+                if (HALO) halo_push_row<T, VX>(P, k, b, j, i0, t0);
             } else if (P.g.flags & FL_AREA) {  // finalize: divide by the cell area (kernels.py:103-104)
                 T ar[VX];
                 Ld<T, VX>::go(plane_base<T>(P.plane[1], b) + (int64_t)j * P.plane[1].pitch + i0, ar);

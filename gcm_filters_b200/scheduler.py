@@ -237,3 +237,151 @@ class BandedFilter:
         outs = tuple(bar[k].reshape(tuple(st["batch_shape"]) + (st["nyl"], st["nx"])).cpu().numpy()
                      for k in range(st["ncomp"]))
         return outs, (st["j0"], st["j1"])
+
+
+class PeerBandedFilter(BandedFilter):
+    """Latitude-band decomposition whose ghost-row exchange is fused into the step kernels.
+
+    The band buffers live in *symmetric memory* (``torch.distributed._symmetric_memory``): every rank maps
+    its neighbours' buffers, so ``gcmf_cheb_step_halo`` can store the first / last owned row of each new
+    ``T_i`` straight into the neighbouring GPU's ghost row over NVLink and raise a flag there; the next
+    step on that GPU spins on the flag only in the CTAs that touch ghost rows.  Per Chebyshev step this is
+    ONE kernel launch per rank and no NCCL call (the :class:`BandedFilter` base class needs two pack
+    kernels, a grouped send/recv and two unpack kernels).
+
+    ``memory="local"`` (the default for world == 1 and for the host-emulator tests) keeps the buffers in
+    ordinary memory: a single rank is its own north and south neighbour.
+    """
+
+    FLAG_WORDS = 16  # uint32: [0] from_south, [1] from_north, [2..3] counters, rest padding
+
+    def __init__(self, flt, rank, world, group=None, library=None, device=None, memory=None):
+        super().__init__(flt, rank, world, group=group, library=library, device=device)
+        self.memory = memory or ("symmetric" if self.world > 1 else "local")
+        self._epoch = 0
+        self._keep = []
+
+    def _alloc(self, nbytes):
+        """(local uint8 tensor, [base pointer of that buffer on every rank])"""
+        import torch
+
+        if self.memory == "local":
+            assert self.world == 1, "local memory only supports a single rank (its own neighbour)"
+            t = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            return t, [t.data_ptr()]
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        t = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        t.zero_()
+        hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+        self._keep.append(hdl)
+        return t, [int(p) for p in hdl.buffer_ptrs]
+
+    def stage(self, *fields):
+        import torch
+
+        lap = self.lap
+        ncomp = lap.ncomp
+        assert len(fields) == ncomp
+        f0 = np.asarray(fields[0])
+        ny, nx = f0.shape[-2:]
+        np_dtype = lap.compute_dtype(f0.dtype if f0.dtype.kind == "f" else np.float64)
+        h, _keep, j0, j1, flags = self._plan(np_dtype, ny, nx)
+        nyl = j1 - j0
+        nb = int(np.prod(f0.shape[:-2])) if f0.ndim > 2 else 1
+        tdt = torch.float32 if np_dtype == np.float32 else torch.float64
+        es = np_dtype.itemsize
+        bands = band_rows(ny, self.world)
+        nyl_max = max(b - a for a, b in bands)
+        rows = nyl_max + 2                      # common allocation: ghost row, owned rows, ghost row
+        slab = ncomp * nb * rows * nx           # elements of one ghosted array
+        slab_bytes = (slab * es + 255) // 256 * 256
+        flag_off = 3 * slab_bytes
+        total = flag_off + 4 * self.FLAG_WORDS
+        buf, bases = self._alloc(total)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+        def view(k):
+            return buf[k * slab_bytes:k * slab_bytes + slab * es].view(tdt).view(ncomp, nb, rows, nx)
+
+        X, A, B = view(0), view(1), view(2)
+        X0 = torch.zeros((ncomp, nb, nyl, nx), dtype=tdt, device=self.device)
+        for k, f in enumerate(fields):
+            band = np.ascontiguousarray(np.asarray(f).reshape((nb, ny, nx))[:, j0:j1])
+            X0[k] = torch.as_tensor(band).to(device=self.device, dtype=tdt)
+        ring = bool(lap._planes.flags & _cabi.FLAG_WRAP_Y) and not (lap._planes.flags & _cabi.FLAG_CUT_S)
+        north = (self.rank + 1) % self.world if (ring or self.rank != self.world - 1) else None
+        south = (self.rank - 1) % self.world if (ring or self.rank != 0) else None
+        st = dict(h=h, flags=flags, j0=j0, j1=j1, nyl=nyl, nb=nb, nx=nx, ncomp=ncomp, X0=X0, X=X, A=A, B=B, buf=buf,
+                  bar=torch.empty((ncomp, nb, nyl, nx), dtype=tdt, device=self.device), batch_shape=f0.shape[:-2],
+                  bases=bases, slab_bytes=slab_bytes, flag_off=flag_off, rows=rows, es=es, north=north, south=south,
+                  nyl_north=(bands[north][1] - bands[north][0]) if north is not None else 0,
+                  nyl_south=(bands[south][1] - bands[south][0]) if south is not None else 0)
+        return st
+
+    def _halo(self, st, which, wait_value, signal_value, push=True):
+        """gcmf_halo for the array in slab `which` (0 = X, 1 = A, 2 = B)."""
+        es, nx, rows, nb, ncomp = st["es"], st["nx"], st["rows"], st["nb"], st["ncomp"]
+        comp = nb * rows * nx * es  # bytes of one component of a ghosted array
+        me = st["bases"][self.rank if self.memory != "local" else 0]
+        hl = _cabi.Halo()
+        hl.north_bstride = hl.south_bstride = rows * nx
+        fl = me + st["flag_off"]
+        hl.counters = fl + 8
+        hl.wait_value, hl.signal_value = wait_value, signal_value
+        for side, peer in (("north", st["north"]), ("south", st["south"])):
+            if peer is None:
+                continue
+            pb = st["bases"][peer if self.memory != "local" else 0]
+            arr = pb + which * st["slab_bytes"]
+            if side == "north":  # my row ny-1 -> north neighbour's row -1 (index 0 of its ghosted array)
+                if push:
+                    for k in range(ncomp):
+                        hl.north_ghost[k] = arr + k * comp
+                hl.wait_north = fl + 4                 # my flag[1]: raised by the north neighbour
+                hl.signal_north = pb + st["flag_off"]  # its flag[0] ("from south")
+            else:                # my row 0 -> south neighbour's row ny_south (index nyl_south + 1)
+                if push:
+                    for k in range(ncomp):
+                        hl.south_ghost[k] = arr + k * comp + (st["nyl_south"] + 1) * nx * es
+                hl.wait_south = fl
+                hl.signal_south = pb + st["flag_off"] + 4
+        return hl
+
+    def run(self, st):
+        import torch
+
+        lib = self.lib
+        h, flags, nyl, nb, nx, ncomp = st["h"], st["flags"], st["nyl"], st["nb"], st["nx"], st["ncomp"]
+        n = int(self.spec.n_steps)
+        es = st["es"]
+        X, A, B, bar = st["X"], st["A"], st["B"], st["bar"]
+        slab = {id(X): 0, id(A): 1, id(B): 2}
+        base = self._epoch * (n + 1)  # flags only grow: value of (epoch, step s) is base + s + 1
+        self._epoch += 1
+        X[:, :, 1:nyl + 1].copy_(st["X0"])
+        rows = st["rows"]
+
+        def inner(t):
+            return [(t[k].data_ptr() + nx * es, nx, rows * nx) for k in range(ncomp)]
+
+        def plain(t):
+            return [(t[k].data_ptr(), nx, nyl * nx) for k in range(ncomp)]
+
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+        if flags & _AREA_FLAG:
+            lib.prepare(h, nb, inner(X), inner(B), stream)
+            X, B = B, X
+        # ghost rows of the prepared input; waits until the neighbours have finished the previous run
+        lib.halo_push(h, nb, inner(X), self._halo(st, slab[id(X)], base, base + 1), stream)
+        lib.cheb_step_halo(h, nb, 1, inner(X), None, inner(A), plain(bar),
+                           self._halo(st, slab[id(A)], base + 1, base + 2), stream)
+        T1, T2 = A, X
+        for i in range(2, n + 1):
+            D = T2
+            hl = self._halo(st, slab[id(D)], base + i, base + i + 1, push=i < n)
+            lib.cheb_step_halo(h, nb, i, inner(T1), inner(T2), inner(D), plain(bar), hl, stream)
+            T2, T1 = T1, D
+        return bar

@@ -158,6 +158,34 @@ int gcmf_cheb_fused(gcmf_plan *plan, int64_t nb, int32_t step, int32_t k, const 
                     const gcmf_field *t2_in, const gcmf_field *t1_out, const gcmf_field *t2_out,
                     const gcmf_field *bar, void *stream);
 
+/* ---- ghost-row exchange through peer memory (latitude-band decomposition over NVLink) ----------------------
+ * No counterpart in the reference (it cannot split the filtered dimensions at all).  A band-decomposed plan
+ * (GCMF_FLAG_WRAP_Y clear) owns rows 0..ny-1 and reads ghost rows -1 and ny.  With a gcmf_halo the step kernel
+ * itself stores its first / last row of T_i into the neighbouring GPUs' ghost rows (plain stores to
+ * peer-mapped addresses) and raises a flag in the neighbour's memory; the next step over there waits for the
+ * flag before touching its ghost rows.  No separate pack / send / receive / unpack launches, no host round trip.
+ * All pointers are device pointers; `north_ghost` / `south_ghost` / `signal_*` point into the NEIGHBOURS'
+ * memory (peer mapped, e.g. torch symmetric memory or CUDA IPC), `wait_*` and `counters` are local.
+ * Flag protocol: flags only grow; a launch waits until *wait_x - wait_value >= 0 (as int32) and, when all of
+ * its border CTAs have pushed, sets *signal_x = signal_value.  NULL pointers disable a direction. */
+typedef struct gcmf_halo {
+    void *north_ghost[2];          /* per component: neighbour's ghost row mirroring my row ny-1 (b = 0, i = 0) */
+    void *south_ghost[2];          /* neighbour's ghost row mirroring my row 0 */
+    int64_t north_bstride, south_bstride; /* batch strides (elements) of the neighbours' arrays */
+    const uint32_t *wait_north, *wait_south;
+    uint32_t *signal_north, *signal_south;
+    uint32_t wait_value, signal_value;
+    uint32_t *counters;            /* local scratch, 2 x uint32, zero before first use */
+} gcmf_halo;
+
+/* gcmf_cheb_step with the exchange fused in: waits for the ghost rows of `t1_in`, computes step `step`, pushes
+ * the border rows of T_step into the neighbours' `t0_out` ghost rows, signals.  The last step pushes nothing
+ * but still signals (so that the neighbours know this rank has finished reading). */
+int gcmf_cheb_step_halo(gcmf_plan *plan, int64_t nb, int32_t step, const gcmf_field *t1_in, const gcmf_field *t2,
+                        const gcmf_field *t0_out, const gcmf_field *bar, const gcmf_halo *halo, void *stream);
+/* Push the border rows of `field` (the prepared input, before step 1) into the neighbours' ghost rows. */
+int gcmf_halo_push(gcmf_plan *plan, int64_t nb, const gcmf_field *field, const gcmf_halo *halo, void *stream);
+
 /* x = field * area (AreaWeightedMixin.prepare, kernels.py:100-101); a copy when the plan has no
  * GCMF_FLAG_AREA.  gcmf_filter calls this itself. */
 int gcmf_prepare(gcmf_plan *plan, int64_t nb, const gcmf_field *in, const gcmf_field *out, void *stream);

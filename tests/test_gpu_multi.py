@@ -27,7 +27,7 @@ def _worker(rank, world, port, g, shape, q):
     import torch
     import torch.distributed as dist
     from gcm_filters_b200 import Filter, FilterShape, GridType
-    from gcm_filters_b200.scheduler import BandedFilter, apply_batch_sharded
+    from gcm_filters_b200.scheduler import BandedFilter, PeerBandedFilter, apply_batch_sharded
     from oracle import fixtures
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -48,6 +48,12 @@ def _worker(rank, world, port, g, shape, q):
             single = (flt.apply(fields[0], dims=["y", "x"]),)
         outs, (j0, j1) = BandedFilter(flt, rank, world).apply(*fields)
         ok = all(np.array_equal(o, s[..., j0:j1, :], equal_nan=True) for o, s in zip(outs, single))
+        # the same decomposition with the ghost-row exchange fused into the kernels (peer memory over NVLink)
+        pbf = PeerBandedFilter(flt, rank, world)
+        for _ in range(3):  # several epochs: the flags only grow
+            pouts, (pj0, pj1) = pbf.apply(*fields)
+        ok = ok and (pj0, pj1) == (j0, j1) and all(np.array_equal(o, s[..., j0:j1, :], equal_nan=True)
+                                                   for o, s in zip(pouts, single))
         # batch sharding with an all-gather of the slabs
         full = (apply_batch_sharded(lambda a: flt.apply(a, None), fields[0], rank, world, gather=True)
                 if len(fields) == 1 else None)
