@@ -437,6 +437,9 @@ def banded_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ms, launches = float(tmax[0].item()), int(t[1].item())
         dist.barrier()
+        if hasattr(bf, "close"):
+            st = None
+            bf.close()
         dist.destroy_process_group()
     clocks = sampler.stop() if sampler else None
     if rank != 0:

@@ -193,10 +193,10 @@ template <typename T> __device__ __forceinline__ void halo_wait(const HaloRef<T>
         unsigned spins = 0;
         if (bottom && h.wait_s)
             while ((int32_t)(ld_acquire_sys(h.wait_s) - h.wait_v) < 0)
-                if (++spins > (1u << 30)) asm volatile("trap;");
+                if (++spins > (1u << 26)) asm volatile("trap;");
         if (top && h.wait_n)
             while ((int32_t)(ld_acquire_sys(h.wait_n) - h.wait_v) < 0)
-                if (++spins > (1u << 30)) asm volatile("trap;");
+                if (++spins > (1u << 26)) asm volatile("trap;");
     }
     __syncthreads();
 }

@@ -260,15 +260,36 @@ class PeerBandedFilter(BandedFilter):
         self.memory = memory or ("symmetric" if self.world > 1 else "local")
         self._epoch = 0
         self._keep = []
+        self._buffers = {}
+
+    def close(self):
+        """Drop the symmetric-memory mappings.  Call before ``destroy_process_group()``: the handles must not
+        outlive the process group they were established on."""
+        import gc
+
+        self._buffers.clear()
+        self._keep.clear()
+        gc.collect()
 
     def _alloc(self, nbytes):
         """(local uint8 tensor, [base pointer of that buffer on every rank])"""
         import torch
 
+        if nbytes in self._buffers:  # one allocation (and one rendezvous) per geometry
+            t, ptrs = self._buffers[nbytes]
+            t.zero_()
+            self._epoch = 0
+            if self.memory != "local":
+                import torch.distributed as dist
+
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)  # nobody may still be signalling into the old contents
+            return t, ptrs
         if self.memory == "local":
             assert self.world == 1, "local memory only supports a single rank (its own neighbour)"
             t = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
-            return t, [t.data_ptr()]
+            self._buffers[nbytes] = (t, [t.data_ptr()])
+            return self._buffers[nbytes]
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -276,7 +297,8 @@ class PeerBandedFilter(BandedFilter):
         t.zero_()
         hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
         self._keep.append(hdl)
-        return t, [int(p) for p in hdl.buffer_ptrs]
+        self._buffers[nbytes] = (t, [int(p) for p in hdl.buffer_ptrs])
+        return self._buffers[nbytes]
 
     def stage(self, *fields):
         import torch

@@ -54,6 +54,7 @@ def _worker(rank, world, port, g, shape, q):
             pouts, (pj0, pj1) = pbf.apply(*fields)
         ok = ok and (pj0, pj1) == (j0, j1) and all(np.array_equal(o, s[..., j0:j1, :], equal_nan=True)
                                                    for o, s in zip(pouts, single))
+        pbf.close()
         # batch sharding with an all-gather of the slabs
         full = (apply_batch_sharded(lambda a: flt.apply(a, None), fields[0], rank, world, gather=True)
                 if len(fields) == 1 else None)
