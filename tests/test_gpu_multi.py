@@ -42,6 +42,10 @@ def _worker(rank, world, port, g, shape, q):
             dxm = float(min(gv["dxT"].min(), gv["dyT"].min()))
             fa = dict(filter_scale=6.0 * dxm, dx_min=dxm)
         flt = Filter(grid_type=GridType[g], grid_vars=gv, filter_shape=FilterShape.GAUSSIAN, **fa)
+        # reference = the one-step kernels on one GPU (the fused path differs in the last bits next to a tripolar
+        # fold, where mirrored cells sum their fluxes in the opposite order)
+        from gcm_filters_b200 import engine
+        engine.set_steps_per_block(1)
         if len(fields) == 2:
             single = flt.apply_to_vector(fields[0], fields[1], dims=["y", "x"])
         else:
