@@ -268,6 +268,22 @@ def _pipeline_chunk(nb, slice_bytes):
     return chunk
 
 
+def _chunk_schedule(nb, chunk):
+    """Batch chunk sizes for the pipeline: small chunks at both ends shorten the ramp (the first H2D copy and
+    the last D2H copy cannot overlap with anything), full-size chunks in between keep the launches long."""
+    ramp = [s for s in (max(1, chunk // 4), max(1, chunk // 2)) if s < chunk]
+    if nb < 2 * sum(ramp) + 2 * chunk:
+        ramp = []
+    sizes, left = list(ramp), nb - 2 * sum(ramp)
+    while left > 0:
+        n = min(chunk, left)
+        sizes.append(n)
+        left -= n
+    sizes += ramp[::-1]
+    assert sum(sizes) == nb
+    return sizes
+
+
 def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
     torch = _torch()
     ncomp = lap.ncomp
@@ -309,9 +325,8 @@ def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
     ev_comp = [torch.cuda.Event() for _ in range(nbuf)]
     ev_d2h = [torch.cuda.Event() for _ in range(nbuf)]
     s_h2d.wait_stream(s_comp)
-    starts = list(range(0, nb, chunk))
-    for i, b0 in enumerate(starts):
-        n = min(chunk, nb - b0)
+    b0 = 0
+    for i, n in enumerate(_chunk_schedule(nb, chunk)):
         k = i % nbuf
         with torch.cuda.stream(s_h2d):
             if i >= nbuf:
@@ -333,30 +348,44 @@ def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
             for cc in range(ncomp):
                 host_out[cc][b0:b0 + n].copy_(dout[k][cc][:n], non_blocking=True)
             ev_d2h[k].record(s_d2h)
+        b0 += n
     s_d2h.synchronize()
     s_comp.wait_stream(s_d2h)
     return tuple(results)
 
 
+def _wants_pipeline(lap, fields, out):
+    """Stream the batch through the device in chunks?  Only for host-resident inputs (and outputs) with a
+    batch axis long enough to overlap copies with compute, and 2-D (shared) coefficient planes."""
+    f0 = fields[0]
+    if _is_torch(f0) and f0.device.type != "cpu":
+        return None
+    if out is not None:
+        o0 = out[0] if isinstance(out, (tuple, list)) else out
+        if _is_torch(o0) and o0.is_cuda:
+            return None
+    shape = tuple(f0.shape)
+    if len(shape) <= 2 or len(fields) != lap.ncomp or any(tuple(f.shape) != shape for f in fields):
+        return None
+    in_dtype = np.dtype(str(f0.dtype).replace("torch.", "")) if _is_torch(f0) else np.asarray(f0).dtype
+    if in_dtype.kind != "f" or in_dtype.itemsize not in (4, 8):
+        in_dtype = np.dtype(np.float64)
+    np_dtype = lap.compute_dtype(in_dtype)
+    planes = [pl for pl in lap._planes.planes if pl is not None] + ([lap._planes.mask] if lap._planes.mask is not None else [])
+    if any(np.ndim(pl) > 2 for pl in planes):
+        return None
+    nb = int(np.prod(shape[:-2]))
+    if nb < PIPELINE_MIN_CHUNKS * _pipeline_chunk(nb, shape[-2] * shape[-1] * np_dtype.itemsize):
+        return None
+    return shape, np_dtype
+
+
 def run_filter(lap, p, c, fields, out=None):
     """filtered = filter_func(fields) on the GPU: prepare, n_steps Chebyshev steps, finalize."""
     torch = _torch()
-    f0 = fields[0]
-    on_host = (not _is_torch(f0)) or f0.device.type == "cpu"
-    if on_host and len(fields) == lap.ncomp and (out is None or not (_is_torch(out[0] if isinstance(out, (tuple, list)) else out)
-                                                                    and (out[0] if isinstance(out, (tuple, list)) else out).is_cuda)):
-        shape = tuple(f0.shape)
-        if len(shape) > 2:
-            nb = int(np.prod(shape[:-2]))
-            in_dtype = np.dtype(str(f0.dtype).replace("torch.", "")) if _is_torch(f0) else np.asarray(f0).dtype
-            if in_dtype.kind != "f" or in_dtype.itemsize not in (4, 8):
-                in_dtype = np.dtype(np.float64)
-            np_dtype = lap.compute_dtype(in_dtype)
-            shared_planes = all(np.ndim(pl) <= 2 for pl in lap._planes.planes if pl is not None) and \
-                (lap._planes.mask is None or np.ndim(lap._planes.mask) <= 2)
-            chunk = _pipeline_chunk(nb, shape[-2] * shape[-1] * np_dtype.itemsize)
-            if shared_planes and nb >= PIPELINE_MIN_CHUNKS * chunk and all(tuple(f.shape) == shape for f in fields):
-                return _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype)
+    piped = _wants_pipeline(lap, fields, out)
+    if piped is not None:
+        return _run_filter_pipelined(lap, p, c, fields, out, *piped)
     st = _Staged(lap, fields)
     plan = device_plan(lap, st.device.index, st.np_dtype, st.ny, st.nx)
     plan.check_batch(st.batch_shape)

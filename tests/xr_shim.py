@@ -79,15 +79,23 @@ def apply_ufunc(func, *args, input_core_dims, output_core_dims, output_dtypes=No
     return outs[0] if single else outs
 
 
+_previous = None
+
+
 def install():
-    """Register the shim as the module `xarray` (only if the real one is missing). Returns the module."""
-    try:
-        import xarray as xr
-        if not getattr(xr, "__gcmf_shim__", False):
+    """Register the shim as the module `xarray` unless the real package is importable.  (The oracle's
+    reference loader may have left its own minimal stub there: it is put back by uninstall().)"""
+    global _previous
+    existing = sys.modules.get("xarray")
+    if existing is None:
+        try:
+            import xarray as xr
             return xr
-        return xr
-    except ImportError:
-        pass
+        except ImportError:
+            pass
+    elif hasattr(existing, "apply_ufunc") and not getattr(existing, "__gcmf_shim__", False):
+        return existing  # the real xarray
+    _previous = existing if existing is not None and not getattr(existing, "__gcmf_shim__", False) else _previous
     mod = types.ModuleType("xarray")
     mod.Variable, mod.DataArray, mod.Dataset, mod.apply_ufunc = Variable, DataArray, Dataset, apply_ufunc
     mod.__gcmf_shim__ = True
@@ -96,6 +104,11 @@ def install():
 
 
 def uninstall():
+    global _previous
     mod = sys.modules.get("xarray")
     if mod is not None and getattr(mod, "__gcmf_shim__", False):
-        del sys.modules["xarray"]
+        if _previous is not None:
+            sys.modules["xarray"] = _previous
+        else:
+            del sys.modules["xarray"]
+    _previous = None
