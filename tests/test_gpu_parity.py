@@ -353,3 +353,29 @@ def test_fused_neighbour_sync_is_deterministic():
     for rep in range(25):
         out = flt.apply(t, None)
         assert torch.equal(torch.nan_to_num(out, nan=-1.0), torch.nan_to_num(plain, nan=-1.0)), rep
+
+
+def test_full_size_pop_slice_vs_oracle_and_properties():
+    """BASELINE config 3 at its full horizontal size (2400 x 3600, fp64, NaN on land), two levels: the fused
+    CUDA path against the oracle (12 forced steps keep the numpy run short), plus size-independent properties."""
+    cfg = fixtures.cfg3(nb=2)
+    (f,), gv = cfg["fields"], cfg["grid_vars"]
+    fa = dict(filter_scale=36.0, dx_min=0.9, filter_shape=FilterShape.GAUSSIAN, n_steps=12)
+    with pytest.warns(UserWarning, match="n_steps below the default"):
+        flt = Filter(grid_type=GridType.IRREGULAR_WITH_LAND, grid_vars=gv, **fa)
+    got = flt.apply(f, None)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = np_oracle.apply_filter("IRREGULAR_WITH_LAND", gv, (f[:1],), filter_scale=36.0, dx_min=0.9, n_steps=12)
+    assert np.array_equal(np.isnan(got[:1]), np.isnan(ref))
+    assert rel_l2(got[:1], ref) < TOL64
+    wet = gv["wet_mask"] == 1
+    # the filter conserves the area integral (reference tests/test_filter.py:118-121) ...
+    area = gv["area"]
+    np.testing.assert_allclose(np.sum((got[1] * area)[wet]), np.sum((f[1] * area)[wet]), rtol=1e-10)
+    # ... leaves a constant untouched and is linear
+    const = np.where(wet, 3.25, np.nan)[None]
+    np.testing.assert_allclose(flt.apply(const, None)[0][wet], 3.25, rtol=1e-13)
+    mix = flt.apply(2.0 * f[:1] - 0.5 * f[1:], None)
+    assert rel_l2(mix[0][wet], (2.0 * got[0] - 0.5 * got[1])[wet]) < 1e-12
