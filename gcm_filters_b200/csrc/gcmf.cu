@@ -658,7 +658,7 @@ extern "C" int gcmf_cheb_step_halo(gcmf_plan* p, int64_t nb, int32_t step, const
 template <typename T> static int fused_kind_t(const gcmf_plan* p) {
     using G = FusedGeom<T>;
     const int fl = p->desc.flags;
-    if (p->desc.nx % G::VX || p->desc.nx < G::TW || p->desc.ny < G::TH) return -1;
+    if (p->desc.nx % G::AV || p->desc.nx < G::TW || p->desc.ny < G::TH) return -1;
     const int tripolar = GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S;  // both or neither: a whole (un-banded) tripolar grid
     if ((fl & tripolar) != 0 && (fl & tripolar) != tripolar) return -1;
     const int base = fl & ~tripolar;
@@ -666,7 +666,7 @@ template <typename T> static int fused_kind_t(const gcmf_plan* p) {
         if (base != (GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM)) return -1;
         for (int s = 0; s < 3; ++s)
             if (!p->plane[s].p || p->plane[s].nb != 1 ||
-                !aligned(p->plane[s].p, p->plane[s].pitch, 0, G::VX, sizeof(T)))
+                !aligned(p->plane[s].p, p->plane[s].pitch, 0, G::AV, sizeof(T)))
                 return -1;
         return FK_FLUX;
     }
@@ -685,9 +685,9 @@ static bool fused_eligible(const gcmf_plan* p) { return fused_kind(p) >= 0; }
 
 #ifdef GCMF_HOSTEMU
 template <typename T, int KIND, bool EDGE> static void fused_host_t(const FusedParams<T>& P, int ncta) {
-    using G = FusedGeom<T>;
+    using G = FusedGeom<T, FusedSplit<KIND>::value>;
     std::vector<T> smem((size_t)G::ntiles(KIND) * G::PLANE);
-    std::vector<FusedThread<T>> st(G::NTHREADS);
+    std::vector<typename FusedTile<T, KIND, EDGE>::Thread> st(G::NTHREADS);
     const int ntiles = P.ncx * P.ncy;
     for (int cta = 0; cta < ncta; ++cta) {
         const int tile = cta % ntiles, grp = cta / ntiles;
@@ -718,7 +718,7 @@ template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, 
 #else
 template <typename T, int KIND, bool EDGE>
 static int launch_fused_kernel_t(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
-    using G = FusedGeom<T>;
+    using G = FusedGeom<T, FusedSplit<KIND>::value>;
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(fused_kernel<T, KIND, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -744,13 +744,13 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
     const bool first = step0 == 1, last = step0 + k - 1 == pl->n_steps;
     const gcmf_field* all[5] = {t1, first ? nullptr : t2, last ? nullptr : t1o, last ? nullptr : t2o, bar};
     for (const gcmf_field* f : all)
-        if (f && !aligned(f->ptr, f->pitch, f->bstride, G::VX, sizeof(T)))
+        if (f && !aligned(f->ptr, f->pitch, f->bstride, G::AV, sizeof(T)))
             return gcmf_set_error(GCMF_EINVAL, "fused step: fields must be 16-byte aligned with vector-multiple strides");
     if (!last && (t1o->ptr == t1->ptr || t2o->ptr == t1->ptr || (!first && (t1o->ptr == t2->ptr || t2o->ptr == t2->ptr))))
         return gcmf_set_error(GCMF_EINVAL, "fused step: outputs must not alias inputs (neighbouring tiles read them)");
     if (bar->ptr == t1->ptr) return gcmf_set_error(GCMF_EINVAL, "fused step: bar must not alias the input");
     if (last && (pl->desc.flags & GCMF_FLAG_AREA) &&
-        (pl->plane[1].nb != 1 || !aligned(pl->plane[1].p, pl->plane[1].pitch, 0, G::VX, sizeof(T))))
+        (pl->plane[1].nb != 1 || !aligned(pl->plane[1].p, pl->plane[1].pitch, 0, G::AV, sizeof(T))))
         return gcmf_set_error(GCMF_EINVAL, "fused step: the area plane must be a shared, vector-aligned 2-D plane");
     FusedParams<T> P;
     memset(&P, 0, sizeof P);

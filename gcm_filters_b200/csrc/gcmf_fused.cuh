@@ -33,10 +33,18 @@ namespace gcmf {
 
 enum : int { FK_FLUX = 0, FK_REG5 = 1 };
 
-template <typename T> struct FusedGeom {
-    static constexpr int VX = 16 / (int)sizeof(T);  // one 16-byte vector per thread and row
-    static constexpr int H = 4;                     // halo width = max fused steps
-    static constexpr int NTX = 64;                  // threads along x
+constexpr int FUSED_H = 4;  // halo width = max fused steps
+
+// XS: how the tile row is split over threads.  1: one 16-byte vector per thread and row (512 threads, used by
+// the register-heavy FLUX kernel); 2: half a vector (1024 threads: the light REGULAR5 steps hide their latency
+// better with twice the warps -- measured +8 % on cfg2, while FLUX loses 30 % with 64 registers per thread).
+template <int KIND> struct FusedSplit { static constexpr int value = KIND == 1 /* FK_REG5 */ ? 2 : 1; };
+
+template <typename T, int XS = 1> struct FusedGeom {
+    static constexpr int AV = 16 / (int)sizeof(T);  // elements per 16 bytes: alignment unit of the bulk copies
+    static constexpr int VX = AV / XS;              // consecutive columns per thread
+    static constexpr int H = FUSED_H;
+    static constexpr int NTX = 64 * XS;             // threads along x
     static constexpr int TW = NTX * VX;             // tile width  incl. halo: 128 (f64) / 256 (f32)
     static constexpr int R = 4;                     // consecutive rows per thread
     static constexpr int NTY = 8;                   // threads along y
@@ -59,7 +67,7 @@ template <typename T> struct FusedParams {
     FieldRef<T> t2_out;         // T_{i+k-2}
     FieldRef<T> bar;            // bar += sum_s p[s] T_{i+s}
     double c;
-    double p[FusedGeom<T>::H];  // Chebyshev coefficients of the k steps
+    double p[FUSED_H];          // Chebyshev coefficients of the k steps
     int32_t k;                  // fused steps, 1..H
     int32_t first;              // block starts at recurrence step 1: t1_in = prepared field x, no T_{i-2}, no bar yet
     int32_t last;               // block ends at step n_steps: bar is finalized (/area) and no T is stored
@@ -69,10 +77,10 @@ template <typename T> struct FusedParams {
     int32_t levels_per_cta;
 };
 
-template <typename T> struct FusedThread {  // per-thread registers that live across phases
-    T t1[FusedGeom<T>::R][FusedGeom<T>::VX];   // raw T_{i-1} of the own points
-    T t2[FusedGeom<T>::R][FusedGeom<T>::VX];   // raw T_{i-2}
-    T acc[FusedGeom<T>::R][FusedGeom<T>::VX];  // running bar (owned points)
+template <typename T, int XS> struct FusedThread {  // per-thread registers that live across phases
+    T t1[FusedGeom<T, XS>::R][FusedGeom<T, XS>::VX];   // raw T_{i-1} of the own points
+    T t2[FusedGeom<T, XS>::R][FusedGeom<T, XS>::VX];   // raw T_{i-2}
+    T acc[FusedGeom<T, XS>::R][FusedGeom<T, XS>::VX];  // running bar (owned points)
     uint32_t mbits;                             // REG5: wet bit of own point (q*VX+v)
     uint64_t wfbits;                            // REG5: wet_fac (0..4) of own point, 4 bits each
 };
@@ -136,7 +144,9 @@ GCMF_HD void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
 
 // EDGE = false: a block strictly inside the recurrence (P.first and P.last are known to be 0 at compile time)
 template <typename T, int KIND, bool EDGE> struct FusedTile {
-    using G = FusedGeom<T>;
+    static constexpr int XS = FusedSplit<KIND>::value;
+    using G = FusedGeom<T, XS>;
+    using Thread = FusedThread<T, XS>;
     const FusedParams<T>& P;
     int gy0, gx0;      // global coordinates of tile element (0,0) (may be negative: wraps)
     int cy0, cx0;      // global coordinates of the first core element
@@ -239,7 +249,7 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     GCMF_HD bool owns_row(int lr) const { return lr >= G::H && lr < G::TH - G::H && (cy0 + lr - G::H) < P.g.ny; }
 
     // phase (once per CTA, REG5 masked): wet bit and wet_fac of the own points from the global uint8 mask
-    GCMF_HD void load_mask(int tid, FusedThread<T>& st) const {
+    GCMF_HD void load_mask(int tid, Thread& st) const {
         st.mbits = 0xffffffffu;
         st.wfbits = 0x4444444444444444ull;  // unmasked: every neighbour is wet
         if (KIND != FK_REG5 || !masked) return;
@@ -274,7 +284,7 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     }
 
     // phase: bar of the owned points from HBM into registers
-    GCMF_HD void load_bar(int tid, int64_t level, FusedThread<T>& st) const {
+    GCMF_HD void load_bar(int tid, int64_t level, Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         const bool oc = owns_cols(tx);
@@ -292,7 +302,7 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     }
 
     // phase: lift the raw own points out of the landing tiles, publish the sanitized T1 in S0
-    GCMF_HD void extract(int tid, FusedThread<T>& st) const {
+    GCMF_HD void extract(int tid, Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         const T* X = tileX();
@@ -321,7 +331,7 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     // every s <= H (threads with 0 < ty < NTY-1), which removes every branch from the row loop.
     template <bool ALLROWS>
     GCMF_HD void step_rows(int tid, int s, const T* __restrict__ S, T* __restrict__ D, T (&X1)[G::R][G::VX],
-                           T (&X2)[G::R][G::VX], FusedThread<T>& st) const {
+                           T (&X2)[G::R][G::VX], Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         const int lr0 = ty * G::R;
@@ -409,7 +419,7 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     }
 
     // odd steps read T_{i-1} from st.t1 and overwrite st.t2; even steps the other way round
-    GCMF_HD void step(int tid, int s, FusedThread<T>& st) const {
+    GCMF_HD void step(int tid, int s, Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         if (lc0 + G::VX <= s || lc0 >= G::TW - s) return;  // column group outside the region
@@ -424,7 +434,7 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     }
 
     // phase: write the owned core points of T_{i+k-1}, T_{i+k-2} and bar back to HBM (from registers)
-    GCMF_HD void store(int tid, int64_t level, const FusedThread<T>& st) const {
+    GCMF_HD void store(int tid, int64_t level, const Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         if (!owns_cols(tx)) return;
         const int lc0 = tx * G::VX;
@@ -458,8 +468,9 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
 
 #ifdef __CUDACC__
 template <typename T, int KIND, bool EDGE>
-__global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const __grid_constant__ FusedParams<T> P) {
-    using G = FusedGeom<T>;
+__global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREADS, 1)
+    fused_kernel(const __grid_constant__ FusedParams<T> P) {
+    using G = FusedGeom<T, FusedSplit<KIND>::value>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
     uint64_t* mb = reinterpret_cast<uint64_t*>(smem_raw + (size_t)G::ntiles(KIND) * G::PLANE * sizeof(T));  // [coef, XY]
@@ -471,7 +482,7 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
     const int64_t l1 = l0 + P.levels_per_cta < P.nb ? l0 + P.levels_per_cta : P.nb;
     if (l0 >= l1) return;
     FusedTile<T, KIND, EDGE> tl(P, tile, smem);
-    FusedThread<T> st;
+    typename FusedTile<T, KIND, EDGE>::Thread st;
     if (tid == 0) {
         mbar_init(&mb[0], G::TH);
         mbar_init(&mb[1], G::TH);
@@ -517,17 +528,19 @@ __global__ void __launch_bounds__(FusedGeom<T>::NTHREADS, 1) fused_kernel(const 
     // group (32 threads x R rows); in phase g (g = it*(k+1) + s, s = 0 for extract) it reads rows published
     // in phase g-1 by the warps above / below it and by the other half of its own rows, and overwrites
     // rows those same warps read in phase g-1.  Both hazards are covered by one rule: start phase g only
-    // when these three warps have completed phase g-1.  Warps therefore drift apart by up to one phase per
+    // when these (up to four) neighbour warps have completed phase g-1.  Warps therefore drift apart by up to one phase per
     // hop, which spreads shared-memory and fp64 work in time instead of convoying at a barrier.
     uint32_t* prog = reinterpret_cast<uint32_t*>(mb + 2);  // [NWARPS] completed-phase counters
     uint32_t* xcount = prog + 32;                           // warps that have drained the landing tiles
     constexpr int NWARPS = G::NTHREADS / 32;
     const int lane = tid & 31, warp = tid >> 5;
-    const int wy = warp >> 1, wh = warp & 1;
-    int nb_warp = -1;  // lanes 0..2 each watch one neighbour warp
-    if (lane == 0) nb_warp = wy * 2 + (wh ^ 1);
-    if (lane == 1 && wy > 0) nb_warp = (wy - 1) * 2 + wh;
-    if (lane == 2 && wy < G::NTY - 1) nb_warp = (wy + 1) * 2 + wh;
+    constexpr int WPR = G::NTX / 32;  // warps per row group
+    const int wy = warp / WPR, wx = warp % WPR;
+    int nb_warp = -1;  // lanes 0..3 each watch one neighbour warp (west, east, south, north)
+    if (lane == 0 && wx > 0) nb_warp = warp - 1;
+    if (lane == 1 && wx < WPR - 1) nb_warp = warp + 1;
+    if (lane == 2 && wy > 0) nb_warp = warp - WPR;
+    if (lane == 3 && wy < G::NTY - 1) nb_warp = warp + WPR;
     auto wait_neighbours = [&](uint32_t need) {
         if (need == 0) return;
         unsigned spins = 0;

@@ -158,6 +158,15 @@ template <> struct Ld<float, 4> {
         o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
     }
 };
+template <> struct Ld<float, 2> {
+    static GCMF_HD void go(const float* p, float (&o)[2]) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        o[0] = t.x; o[1] = t.y;
+    }
+};
+template <> struct St<float, 2> {
+    static GCMF_HD void go(float* p, const float (&o)[2]) { *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]); }
+};
 template <> struct Ld<uint8_t, 4> {
     static GCMF_HD void go(const uint8_t* p, uint8_t (&o)[4]) {
         const uchar4 t = *reinterpret_cast<const uchar4*>(p);
