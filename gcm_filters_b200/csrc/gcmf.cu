@@ -785,6 +785,10 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
     if (groups < 1) groups = 1;
     if (groups > nb) groups = nb;
     P.levels_per_cta = (int32_t)((nb + groups - 1) / groups);
+    if (const char* e = getenv("GCMF_FUSED_LEVELS_PER_CTA")) {  // test / tuning knob: force the slab length
+        const long v = atol(e);
+        if (v > 0) P.levels_per_cta = (int32_t)(v < nb ? v : nb);
+    }
     groups = (nb + P.levels_per_cta - 1) / P.levels_per_cta;
     const int64_t ncta = ntiles * groups;
     if (ncta > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "fused step: grid too large");

@@ -46,8 +46,12 @@ template <typename T, int XS = 1> struct FusedGeom {
     static constexpr int H = FUSED_H;
     static constexpr int NTX = 64 * XS;             // threads along x
     static constexpr int TW = NTX * VX;             // tile width  incl. halo: 128 (f64) / 256 (f32)
-    static constexpr int R = 4;                     // consecutive rows per thread
-    static constexpr int NTY = 8;                   // threads along y
+#ifndef GCMF_FUSED_R
+#define GCMF_FUSED_R 4
+#define GCMF_FUSED_NTY 8
+#endif
+    static constexpr int R = GCMF_FUSED_R;          // consecutive rows per thread
+    static constexpr int NTY = GCMF_FUSED_NTY;      // threads along y
     static constexpr int TH = R * NTY;              // tile height incl. halo: 32
     static constexpr int CW = TW - 2 * H;           // core width  120 / 248
     static constexpr int CH = TH - 2 * H;           // core height 24
@@ -203,14 +207,14 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
         bulk_copy_g2s(dst_tile + r * G::TW, row + gx, (unsigned)(n1 * sizeof(T)), mb);
         if (n1 < G::TW) bulk_copy_g2s(dst_tile + r * G::TW + n1, row, (unsigned)((G::TW - n1) * sizeof(T)), mb);
     }
-    // Virtual rows of one tile, gathered by the 32 issuing lanes together (lane strides over the columns).
+    // Virtual rows of one tile, gathered by the TH issuing lanes together (lane strides over the columns).
     GCMF_HD void gather_virtual(int lane, T* dst_tile, const T* src_slice, int64_t pitch, int dj = 0, int di = 0) const {
         if (!fold()) return;
         int r0 = P.g.ny - gy0;  // first virtual tile row
         if (r0 < 0) r0 = 0;
         for (int r = r0; r < G::TH; ++r) {
             const T* row = src_slice + (int64_t)(image_row(r) + dj) * pitch;
-            for (int c = lane; c < G::TW; c += 32) dst_tile[r * G::TW + c] = row[wrap_index(image_col(c) + di, P.g.nx)];
+            for (int c = lane; c < G::TW; c += G::TH) dst_tile[r * G::TW + c] = row[wrap_index(image_col(c) + di, P.g.nx)];
         }
     }
     // phase: thread r < TH stages the coefficient rows (FLUX).  Returns the bulk bytes it issued.
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
         fence_mbar_init();
     }
     if (tid < 40) reinterpret_cast<uint32_t*>(mb + 2)[tid] = 0u;  // progress flags [32] + drain counter
-    static_assert(G::TH == 32, "the landing-tile refill is issued by one warp: one lane per tile row");
+    static_assert(G::TH <= 32 && G::R >= G::H, "one refill lane per tile row; inner threads own only in-region rows");
     __syncthreads();
     if (tid < G::TH) {
         if (KIND == FK_FLUX) {
@@ -569,8 +573,10 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
         old = __shfl_sync(0xffffffffu, old, 0);
         if (old == (uint32_t)NWARPS * (uint32_t)(it + 1) - 1u && l + 1 < l1) {
             fence_proxy_async();
-            tl.issue_state_row(lane, l + 1, &mb[1]);
-            mbar_expect_tx(&mb[1], tl.state_tx_bytes(lane));
+            if (lane < G::TH) {
+                tl.issue_state_row(lane, l + 1, &mb[1]);
+                mbar_expect_tx(&mb[1], tl.state_tx_bytes(lane));
+            }
         }
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {

@@ -379,3 +379,34 @@ def test_full_size_pop_slice_vs_oracle_and_properties():
     np.testing.assert_allclose(flt.apply(const, None)[0][wet], 3.25, rtol=1e-13)
     mix = flt.apply(2.0 * f[:1] - 0.5 * f[1:], None)
     assert rel_l2(mix[0][wet], (2.0 * got[0] - 0.5 * got[1])[wet]) < 1e-12
+
+
+@pytest.mark.parametrize("g,dtype", [("IRREGULAR_WITH_LAND", np.float64), ("REGULAR_WITH_LAND", np.float32),
+                                     ("TRIPOLAR_POP_WITH_LAND", np.float64)])
+@pytest.mark.parametrize("levels", [2, 5])
+def test_fused_level_slabs(g, dtype, levels, monkeypatch):
+    """A CTA that loops over several levels (TMA refill of the landing tiles during the steps, mbarrier parity,
+    growing progress counters): forced here because small grids get one level per CTA on their own; the benchmark
+    configs run with ~30 levels per CTA."""
+    from gcm_filters_b200 import engine
+    shape = (96, 520)
+    (f,), gv = fixtures.fixture(g, shape)
+    rng = np.random.default_rng(levels)
+    fb = (f[None] * (1 + 0.3 * rng.standard_normal((11, 1, 1)))).astype(dtype)
+    fb[:, gv["wet_mask"] == 0] = np.nan
+    gvt = {k: v.astype(dtype) for k, v in gv.items()}
+    flt = make_filter(g, gvt, filter_scale=10.0, dx_min=1.0)
+    import torch
+    dev = torch.as_tensor(fb).cuda()  # device-resident: one launch over all 11 levels (host inputs are chunked)
+    monkeypatch.setenv("GCMF_FUSED_LEVELS_PER_CTA", str(levels))
+    fused = flt.apply(dev, None).cpu().numpy()
+    monkeypatch.delenv("GCMF_FUSED_LEVELS_PER_CTA")
+    try:
+        engine.set_steps_per_block(1)
+        plain = flt.apply(dev, None).cpu().numpy()
+    finally:
+        engine.set_steps_per_block(0)
+    if g.startswith("TRIPOLAR"):
+        assert np.array_equal(np.isnan(fused), np.isnan(plain)) and rel_l2(fused, plain) < 1e-14
+    else:
+        assert np.array_equal(fused, plain, equal_nan=True)

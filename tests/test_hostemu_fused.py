@@ -128,3 +128,31 @@ def test_fused_regular5(g, dtype, shape):
         assert np.array_equal(a, ref, equal_nan=True)  # REGULAR5 family: bit-identical to the reference arithmetic
     else:
         assert rel_l2(a, ref) < 1e-5
+
+
+@pytest.mark.parametrize("g,dtype", [("IRREGULAR_WITH_LAND", np.float64), ("REGULAR_WITH_LAND", np.float32),
+                                     ("TRIPOLAR_POP_WITH_LAND", np.float64)])
+@pytest.mark.parametrize("levels", [2, 3, 7])
+def test_fused_level_slabs(g, dtype, levels, monkeypatch):
+    """One CTA loops over a slab of levels (landing tiles refilled while the steps run, mbarrier parity flips,
+    progress counters keep growing).  Small grids never get slabs longer than one level on their own, so the
+    slab length is forced."""
+    monkeypatch.setenv("GCMF_FUSED_LEVELS_PER_CTA", str(levels))
+    shape = (40, 264)
+    (f,), gv = fixtures.fixture(g, shape)
+    rng = np.random.default_rng(levels)
+    fb = f[None] * (1 + 0.3 * rng.standard_normal((7, 1, 1)))
+    fb[:, gv["wet_mask"] == 0] = np.nan
+    lap = ALL_KERNELS[GridType[g]](**gv)
+    spec = _compute_filter_spec(8.0, 1.0, FilterShape.GAUSSIAN, np.pi, 2, 9)
+    c = _shift_scale(spec, lap)
+    fused = EmuPlan(lap, dtype, *shape)
+    (a,) = fused.filter((fb.astype(dtype),), spec.p, c)
+    monkeypatch.delenv("GCMF_FUSED_LEVELS_PER_CTA")
+    plain = EmuPlan(lap, dtype, *shape)
+    emu_set_steps_per_block(plain, 1)
+    (b,) = plain.filter((fb.astype(dtype),), spec.p, c)
+    if g.startswith("TRIPOLAR"):
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and rel_l2(a, b) < 1e-14
+    else:
+        assert np.array_equal(a, b, equal_nan=True)
