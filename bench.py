@@ -38,7 +38,7 @@ UNIT = "pt-steps/s"
 
 # ------------------------------------------------------------------------------------------ workloads
 def build_workload(name, nb, rank=0):
-    from oracle import fixtures  # deterministic synthetic inputs only (no compute)
+    import bench_inputs as fixtures  # deterministic synthetic inputs (no oracle, no product code)
 
     if name == "cfg3":
         cfg = fixtures.cfg3(nb=nb or 62)

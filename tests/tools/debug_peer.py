@@ -1,6 +1,6 @@
 """Debug driver for PeerBandedFilter on N GPUs (torchrun)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, torch.distributed as dist
 
 def log(*a):

@@ -1,3 +1,5 @@
+"""compute-sanitizer driver: a small case of every kernel family, checked against the oracle.
+    compute-sanitizer --tool memcheck python tests/tools/sanitize_small.py"""
 import sys, numpy as np
 sys.path.insert(0, '.')
 from gcm_filters_b200 import Filter, GridType, engine
