@@ -388,7 +388,7 @@ def banded_arm(args):
     import torch.distributed as dist
 
     from gcm_filters_b200 import Filter, FilterShape, GridType, _cabi
-    from gcm_filters_b200.scheduler import BandedFilter, PeerBandedFilter
+    from gcm_filters_b200.scheduler import BandedFilter, FusedBandedFilter, PeerBandedFilter
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -402,7 +402,8 @@ def banded_arm(args):
     fa["filter_shape"] = FilterShape[fa["filter_shape"]]
     flt = Filter(grid_type=GridType[cfg["grid_type"]], grid_vars=cfg["grid_vars"], **fa)
     n_steps = int(flt.n_steps)
-    bf = PeerBandedFilter(flt, rank, world) if args.peer else BandedFilter(flt, rank, world)
+    cls = FusedBandedFilter if args.fused else (PeerBandedFilter if args.peer else BandedFilter)
+    bf = cls(flt, rank, world)
     st = bf.stage(*cfg["fields"])
     f0 = cfg["fields"][0]
     ny, nx = f0.shape[-2:]
@@ -456,7 +457,8 @@ def banded_arm(args):
         "dtype": "f64" if w == 8 else "f32", "data": "synthetic (numpy PCG64, SURVEY 8(d))",
         "config": dict(workload_descr(cfg, n_steps),
                        sharding=f"{world} latitude band(s), 1 ghost row per side, " +
-                       ("ghost rows stored by the step kernels into the neighbours' peer memory (NVLink), flag-synchronised"
+                       ("4 ghost rows, fused 4-step blocks, one NCCL exchange per block" if args.fused else
+                        "ghost rows stored by the step kernels into the neighbours' peer memory (NVLink), flag-synchronised"
                         if args.peer else "NCCL send/recv per Chebyshev step")),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "step_kernel (one Chebyshev step per launch) + halo exchange, per GPU",
@@ -544,6 +546,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-per-block", type=int, default=0, help="0 auto, 1 = one-step kernels only")
+    ap.add_argument("--fused", action="store_true",
+                    help="with --banded: temporally blocked kernel on the bands, one ghost exchange per 4-step block")
     ap.add_argument("--peer", action="store_true",
                     help="with --banded: ghost rows pushed by the step kernels through peer memory instead of NCCL")
     ap.add_argument("--banded", action="store_true",

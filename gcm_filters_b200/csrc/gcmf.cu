@@ -158,6 +158,7 @@ static size_t buffer_bytes(const gcmf_plan* p, int64_t nb) {
 
 static bool fused_eligible(const gcmf_plan* p);
 static bool plan_uses_fused(const gcmf_plan* p) { return p->steps_per_block != 1 && fused_eligible(p); }
+static bool is_band_plan(const gcmf_plan* p) { return !(p->desc.flags & GCMF_FLAG_WRAP_Y); }
 
 extern "C" int gcmf_plan_set_steps_per_block(gcmf_plan* p, int32_t k) {
     if (!p) return gcmf_set_error(GCMF_EINVAL, "null plan");
@@ -661,7 +662,11 @@ template <typename T> static int fused_kind_t(const gcmf_plan* p) {
     if (p->desc.nx % G::AV || p->desc.nx < G::TW || p->desc.ny < G::TH) return -1;
     const int tripolar = GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S;  // both or neither: a whole (un-banded) tripolar grid
     if ((fl & tripolar) != 0 && (fl & tripolar) != tripolar) return -1;
-    const int base = fl & ~tripolar;
+    // A latitude band (no WRAP_Y) may use the fused path too: the caller keeps FUSED_H ghost rows of the
+    // fields and of every plane on each side of the band and exchanges them after every block.
+    const bool band = !(fl & GCMF_FLAG_WRAP_Y);
+    if (band && (fl & tripolar)) return -1;
+    const int base = (fl & ~tripolar) | GCMF_FLAG_WRAP_Y;
     if (p->desc.op == GCMF_OP_FLUX) {
         if (base != (GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM)) return -1;
         for (int s = 0; s < 3; ++s)
@@ -861,6 +866,9 @@ extern "C" int gcmf_filter(gcmf_plan* p, int64_t nb, const gcmf_field* in, const
         for (int k = 0; k < nc; ++k) X[k] = B[k];
     }
     const int n = p->n_steps;
+    if (is_band_plan(p))
+        return gcmf_set_error(GCMF_EINVAL, "gcmf_filter runs whole (periodic / tripolar) grids; drive a latitude band with "
+                                           "gcmf_cheb_step / gcmf_cheb_fused and exchange its ghost rows between calls");
     if (plan_uses_fused(p)) {
         // Temporally blocked path: the whole recurrence (filter.py:191-206) as ceil(n/kmax) launches; the first
         // block performs step 1, the last one finalizes bar.  State ping-pongs between two workspace pairs.

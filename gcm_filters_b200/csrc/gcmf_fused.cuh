@@ -191,6 +191,15 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     GCMF_HD int image_row(int r) const { return 2 * P.g.ny - 1 - (gy0 + r); }          // real row of a virtual tile row
     GCMF_HD int image_col(int c) const { return P.g.nx - 1 - wrap_index(gx0 + c, P.g.nx); }  // real column
 
+    // Global row of tile row r.  Periodic grids wrap; a latitude band (FL_WRAP_Y clear) has FUSED_H ghost rows
+    // physically present below row 0 and above row ny-1 (rows further out lie outside the dependency cone of
+    // every owned row and are clamped onto the last ghost row).
+    GCMF_HD int source_row(int r) const {
+        const int g = gy0 + r;
+        if (P.g.flags & FL_WRAP_Y) return wrap_index(g, P.g.ny);
+        return g < -G::H ? -G::H : (g > P.g.ny + G::H - 1 ? P.g.ny + G::H - 1 : g);
+    }
+
     // bytes of row r that arrive through bulk copies (the mbarrier's expected transaction count)
     GCMF_HD unsigned row_tx_bytes(int r) const { return virtual_row(r) ? 0u : (unsigned)(G::TW * sizeof(T)); }
 
@@ -200,7 +209,7 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
                           int di = 0) const {
         (void)dj; (void)di;
         if (virtual_row(r)) return;  // gathered cooperatively by gather_virtual()
-        const int gy = wrap_index(gy0 + r, P.g.ny);
+        const int gy = source_row(r);
         const int gx = wrap_index(gx0, P.g.nx);
         const T* row = src_slice + (int64_t)gy * pitch;
         const int n1 = (P.g.nx - gx) < G::TW ? (P.g.nx - gx) : G::TW;
@@ -266,7 +275,7 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
         for (int q = 0; q < G::R; ++q) {
             const int r = ty * G::R + q;
             const bool virt = virtual_row(r);
-            const int gy = virt ? image_row(r) : wrap_index(gy0 + r, ny);
+            const int gy = virt ? image_row(r) : source_row(r);
             for (int v = 0; v < G::VX; ++v) {
                 const int c = tx * G::VX + v;
                 const int gx = virt ? image_col(c) : wrap_index(gx0 + c, nx);
@@ -275,9 +284,10 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
                 if (m[(int64_t)gy * pitch + gx]) mb |= 1u << idx;
                 // north neighbour of the top row is its mirror image across the fold (kernels.py:461-467)
                 const bool top = fold() && gy == ny - 1;
-                const int gyn = top ? ny - 1 : (gy + 1 == ny ? 0 : gy + 1);
+                const bool wrap_y = (P.g.flags & FL_WRAP_Y) != 0;
+                const int gyn = top ? ny - 1 : (wrap_y && gy + 1 == ny ? 0 : gy + 1);
                 const int gxn = top ? nx - 1 - gx : gx;
-                const int gys = gy == 0 ? ny - 1 : gy - 1;  // row 0 of a tripolar grid is land: inert
+                const int gys = wrap_y && gy == 0 ? ny - 1 : gy - 1;  // row 0 of a tripolar grid is land: inert
                 const uint64_t cnt = (m[(int64_t)gy * pitch + gxe] != 0) + (m[(int64_t)gy * pitch + gxw] != 0) +
                                      (m[(int64_t)gyn * pitch + gxn] != 0) + (m[(int64_t)gys * pitch + gx] != 0);
                 wf |= cnt << (4 * idx);

@@ -91,10 +91,10 @@ class BandedFilter:
         self._plans = {}
 
     # ---- band-local plan: planes sliced with one ghost row above and below ---------------------
-    def _plan(self, np_dtype, ny, nx):
+    def _plan(self, np_dtype, ny, nx, halo=1):
         import torch
 
-        key = (np.dtype(np_dtype).str, ny, nx)
+        key = (np.dtype(np_dtype).str, ny, nx, halo)
         if key in self._plans:
             return self._plans[key]
         j0, j1 = band_rows(ny, self.world)[self.rank]
@@ -108,7 +108,7 @@ class BandedFilter:
         dt = engine._DT[np.dtype(np_dtype)]
         dev_index = self.device.index if self.device.type == "cuda" else 0
         h = self.lib.plan_create(spec.op, dt, nyl, nx, flags, dev_index)
-        rows = np.arange(j0 - 1, j1 + 1) % ny
+        rows = np.arange(j0 - halo, j1 + halo) % ny
         tdt = torch.float32 if np.dtype(np_dtype) == np.float32 else torch.float64
         keep = []
         for slot, pl in enumerate(spec.planes):
@@ -119,35 +119,35 @@ class BandedFilter:
             src = np.asarray(src)
             if src.ndim != 2:
                 raise NotImplementedError("band decomposition supports 2-D grid variables")
-            band = np.ascontiguousarray(src[rows])  # (nyl + 2, nx), periodic ghost rows
+            band = np.ascontiguousarray(src[rows])  # (nyl + 2*halo, nx), periodic ghost rows
             t = torch.as_tensor(band).to(device=self.device, dtype=torch.uint8 if is_mask else tdt).contiguous()
             keep.append(t)
-            self.lib.plan_set_plane(h, slot, t.data_ptr() + nx * t.element_size(), nx, (nyl + 2) * nx, 1)
+            self.lib.plan_set_plane(h, slot, t.data_ptr() + halo * nx * t.element_size(), nx, (nyl + 2 * halo) * nx, 1)
         self.lib.plan_set_filter(h, [float(v) for v in self.spec.p], float(self.c))
         self._plans[key] = (h, keep, j0, j1, flags)
         return self._plans[key]
 
-    # ---- ghost-row exchange of a (ncomp, nb, nyl+2, nx) tensor -------------------------------------
-    def _exchange(self, t, ring):
+    # ---- ghost-row exchange of a (ncomp, nb, nyl+2h, nx) tensor with h ghost rows per side ---------------
+    def _exchange(self, t, ring, h=1):
         import torch
         import torch.distributed as dist
 
-        nyl = t.shape[-2] - 2
+        nyl = t.shape[-2] - 2 * h
         north, south = (self.rank + 1) % self.world, (self.rank - 1) % self.world
         has_n = ring or self.rank != self.world - 1
         has_s = ring or self.rank != 0
         if self.world == 1:
             if ring:
-                t[..., 0, :] = t[..., nyl, :]
-                t[..., nyl + 1, :] = t[..., 1, :]
+                t[..., 0:h, :] = t[..., nyl:nyl + h, :]
+                t[..., nyl + h:nyl + 2 * h, :] = t[..., h:2 * h, :]
             return
-        top = t[..., nyl, :].contiguous()      # my northernmost owned row -> north neighbour's south ghost
-        bot = t[..., 1, :].contiguous()        # my southernmost owned row -> south neighbour's north ghost
+        top = t[..., nyl:nyl + h, :].contiguous()  # my northernmost owned rows -> north neighbour's south ghosts
+        bot = t[..., h:2 * h, :].contiguous()      # my southernmost owned rows -> south neighbour's north ghosts
         gn, gs = torch.empty_like(top), torch.empty_like(bot)
         ops = []
         # Ordering matters when north == south (world == 2): NCCL matches the k-th send to a peer with the
-        # k-th receive from it, so sends go (bottom row, top row) against receives (north ghost, south
-        # ghost).  gloo matches by tag.
+        # k-th receive from it, so sends go (bottom rows, top rows) against receives (north ghosts, south
+        # ghosts).  gloo matches by tag.
         if has_s:
             ops.append(dist.P2POp(dist.isend, bot, south, group=self.group, tag=2))
         if has_n:
@@ -158,9 +158,9 @@ class BandedFilter:
         for req in dist.batch_isend_irecv(ops) if ops else []:
             req.wait()
         if has_n:
-            t[..., nyl + 1, :] = gn
+            t[..., nyl + h:nyl + 2 * h, :] = gn
         if has_s:
-            t[..., 0, :] = gs
+            t[..., 0:h, :] = gs
 
     # ---- the filter on this rank's band -----------------------------------------------------------
     def stage(self, *fields):
@@ -406,4 +406,78 @@ class PeerBandedFilter(BandedFilter):
             hl = self._halo(st, slab[id(D)], base + i, base + i + 1, push=i < n)
             lib.cheb_step_halo(h, nb, i, inner(T1), inner(T2), inner(D), plain(bar), hl, stream)
             T2, T1 = T1, D
+        return bar
+
+
+class FusedBandedFilter(BandedFilter):
+    """Latitude bands driven by the temporally blocked kernel: every rank keeps ``H = 4`` ghost rows per side,
+    runs up to four Chebyshev steps per launch (``gcmf_cheb_fused`` on a band plan) and exchanges the ghost
+    rows of ``T_{i+k-1}`` and ``T_{i+k-2}`` **once per block** instead of once per step (north_star item 3:
+    "per-step-block halo exchange").  Scalar FLUX / REGULAR5 operators on doubly periodic grids; the band must
+    be at least one tile high (32 rows) and ``nx`` a multiple of the vector width."""
+
+    def _fused_plan(self, np_dtype, ny, nx):
+        flags_all = self.lap._planes.flags
+        if flags_all & (_cabi.FLAG_FOLD_N | _cabi.FLAG_CUT_S):
+            raise NotImplementedError("fused band decomposition supports doubly periodic grids")
+        H = 4
+        h, keep, j0, j1, flags = self._plan(np_dtype, ny, nx, halo=H)
+        if self.lib.fused_max_steps(h) < H:
+            raise ValueError("this operator / band size has no fused kernel (band >= 32 rows, nx >= one tile, "
+                             "nx a multiple of the 16-byte vector width)")
+        return h, j0, j1, flags, H
+
+    def stage(self, *fields):
+        import torch
+
+        lap = self.lap
+        assert lap.ncomp == 1 and len(fields) == 1, "scalar operators only"
+        f0 = np.asarray(fields[0])
+        ny, nx = f0.shape[-2:]
+        np_dtype = lap.compute_dtype(f0.dtype if f0.dtype.kind == "f" else np.float64)
+        h, j0, j1, flags, H = self._fused_plan(np_dtype, ny, nx)
+        nyl = j1 - j0
+        nb = int(np.prod(f0.shape[:-2])) if f0.ndim > 2 else 1
+        tdt = torch.float32 if np_dtype == np.float32 else torch.float64
+
+        def new():
+            return torch.zeros((1, nb, nyl + 2 * H, nx), dtype=tdt, device=self.device)
+
+        X0 = torch.as_tensor(np.ascontiguousarray(f0.reshape((nb, ny, nx))[:, j0:j1])).to(device=self.device, dtype=tdt)
+        return dict(h=h, flags=flags, j0=j0, j1=j1, nyl=nyl, nb=nb, nx=nx, ncomp=1, H=H, X0=X0, X=new(),
+                    pairs=[[new(), new()], [new(), new()]], P=new(),
+                    bar=torch.empty((1, nb, nyl, nx), dtype=tdt, device=self.device), batch_shape=f0.shape[:-2])
+
+    def run(self, st):
+        import torch
+
+        lib = self.lib
+        h, flags, nyl, nb, nx, H = st["h"], st["flags"], st["nyl"], st["nb"], st["nx"], st["H"]
+        n = int(self.spec.n_steps)
+        X, bar = st["X"], st["bar"]
+        es = X.element_size()
+        rows = nyl + 2 * H
+
+        def inner(t):  # the owned rows start H rows into the ghosted array
+            return [(t[0].data_ptr() + H * nx * es, nx, rows * nx)]
+
+        plain = [(bar[0].data_ptr(), nx, nyl * nx)]
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+        X[0, :, H:H + nyl].copy_(st["X0"])
+        if flags & _AREA_FLAG:  # x = f * area on the owned rows (kernels.py:100-101), then its ghosts
+            lib.prepare(h, nb, inner(X), inner(st["P"]), stream)
+            X = st["P"]
+        self._exchange(X, True, H)
+        T1 = T2 = X
+        cur, i = 0, 1
+        while i <= n:
+            kk = min(H, n - i + 1)
+            O1, O2 = st["pairs"][cur]
+            lib.cheb_fused(h, nb, i, kk, inner(T1), inner(T2), inner(O1), inner(O2), plain, stream)
+            if i + kk <= n:  # the next block reads the ghost rows of both carried fields
+                self._exchange(O1, True, H)
+                self._exchange(O2, True, H)
+            T1, T2 = O1, O2
+            cur ^= 1
+            i += kk
         return bar

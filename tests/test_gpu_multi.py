@@ -27,7 +27,7 @@ def _worker(rank, world, port, g, shape, q):
     import torch
     import torch.distributed as dist
     from gcm_filters_b200 import Filter, FilterShape, GridType
-    from gcm_filters_b200.scheduler import BandedFilter, PeerBandedFilter, apply_batch_sharded
+    from gcm_filters_b200.scheduler import BandedFilter, FusedBandedFilter, PeerBandedFilter, apply_batch_sharded
     from oracle import fixtures
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -59,6 +59,9 @@ def _worker(rank, world, port, g, shape, q):
         ok = ok and (pj0, pj1) == (j0, j1) and all(np.array_equal(o, s[..., j0:j1, :], equal_nan=True)
                                                    for o, s in zip(pouts, single))
         pbf.close()
+        if g == "IRREGULAR_WITH_LAND":  # temporal blocking on bands: 4 ghost rows, one NCCL exchange per block
+            fouts, (fj0, fj1) = FusedBandedFilter(flt, rank, world).apply(*fields)
+            ok = ok and (fj0, fj1) == (j0, j1) and np.array_equal(fouts[0], single[0][..., j0:j1, :], equal_nan=True)
         # batch sharding with an all-gather of the slabs
         full = (apply_batch_sharded(lambda a: flt.apply(a, None), fields[0], rank, world, gather=True)
                 if len(fields) == 1 else None)
@@ -76,7 +79,8 @@ def test_banded_and_sharded_match_single_gpu(g):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, g, (90, 160), q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, g, (90, 160) if g != "IRREGULAR_WITH_LAND" else (96, 264), q))
+             for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

@@ -109,3 +109,49 @@ def test_batch_sharding_gather():
         p.join(60)
         assert p.exitcode == 0
     assert all(ok for _, ok in (q.get(timeout=10) for _ in range(world)))
+
+
+def _fused_band_worker(rank, world, port, g, shape, dtype, q):
+    from gcm_filters_b200.scheduler import FusedBandedFilter
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        (f,), gv = fixtures.fixture(g, shape)
+        fb = np.stack([f, f * f, 1 - f]).astype(dtype)
+        if "wet_mask" in gv:
+            fb[:, gv["wet_mask"] == 0] = np.nan
+        gvt = {k: v.astype(dtype) for k, v in gv.items()}
+        fa = dict(filter_scale=10.0, dx_min=1.0)
+        flt = Filter(grid_type=GridType[g], grid_vars=gvt, filter_shape=FilterShape.GAUSSIAN, **fa)
+        bf = FusedBandedFilter(flt, rank, world, library=emu_library(), device="cpu")
+        for _ in range(2):
+            outs, (j0, j1) = bf.apply(fb)
+        ref = np_oracle.apply_filter(g, gv, (fb.astype(np.float64),), **fa)[..., j0:j1, :]
+        assert np.array_equal(np.isnan(outs[0]), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        err = float(np.linalg.norm(outs[0][ok] - ref[ok]) / np.linalg.norm(ref[ok]))
+        q.put((rank, j0, j1, err))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("g,dtype,tol", [("IRREGULAR_WITH_LAND", np.float64, 1e-12), ("REGULAR_WITH_LAND", np.float64, 1e-15),
+                                         ("REGULAR_WITH_LAND_AREA_WEIGHTED", np.float32, 1e-5)])
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_band_decomposition(g, dtype, tol, world):
+    """Temporal blocking on latitude bands: 4 ghost rows, one exchange per 4-step block."""
+    emu_library()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    shape = (112, 264)
+    procs = [ctx.Process(target=_fused_band_worker, args=(r, world, port, g, shape, dtype, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(world))
+    assert [(r[1], r[2]) for r in res] == band_rows(shape[0], world)
+    assert max(r[3] for r in res) < tol
