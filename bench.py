@@ -456,7 +456,7 @@ def banded_arm(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64" if w == 8 else "f32", "data": "synthetic (numpy PCG64, SURVEY 8(d))",
         "config": dict(workload_descr(cfg, n_steps),
-                       sharding=f"{world} latitude band(s), 1 ghost row per side, " +
+                       sharding=f"{world} latitude band(s), " +
                        ("4 ghost rows, fused 4-step blocks, one NCCL exchange per block" if args.fused else
                         "ghost rows stored by the step kernels into the neighbours' peer memory (NVLink), flag-synchronised"
                         if args.peer else "NCCL send/recv per Chebyshev step")),

@@ -166,6 +166,11 @@ def get_library():
     global _lib
     with _lock:
         if _lib is None:
+            from . import build as _build
+
+            if _build.is_stale():
+                raise GcmfError(f"{LIB_PATH} was built from different sources than the ones in the tree; "
+                                "rebuild with `python -m gcm_filters_b200.build`")
             lib = Library(LIB_PATH)
             if lib.lib.gcmf_sm_arch() != 100:
                 raise GcmfError(f"{LIB_PATH} is not an sm_100a build")

@@ -16,6 +16,32 @@ NVCC_FLAGS = [
 ]
 
 
+HASH = OUT + ".srchash"
+
+
+def source_hash():
+    """sha256 over the CUDA sources, headers and flags: identifies what a built libgcmf.so was made from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for rel in SOURCES + ["gcmf_fused.cuh"] + HEADERS:
+        with open(os.path.join(CSRC, rel), "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_stale():
+    """True when libgcmf.so exists but was built from different sources than the ones in the tree."""
+    if not os.path.isfile(OUT) or not os.path.isfile(HASH):
+        return False
+    try:
+        with open(HASH) as fh:
+            return fh.read().strip() != source_hash()
+    except OSError:
+        return False
+
+
 def find_nvcc():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.isfile(cand):
@@ -24,11 +50,10 @@ def find_nvcc():
 
 
 def up_to_date():
-    if not os.path.isfile(OUT):
+    if not os.path.isfile(OUT) or not os.path.isfile(HASH):
         return False
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
+    with open(HASH) as fh:
+        return fh.read().strip() == source_hash()
 
 
 def build(force=False, verbose=False):
@@ -38,6 +63,8 @@ def build(force=False, verbose=False):
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(HASH, "w") as fh:
+        fh.write(source_hash())
     if verbose:
         print(res.stderr)
     return OUT
