@@ -779,12 +779,15 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
     P.ncx = (pl->desc.nx + G::CW - 1) / G::CW;
     P.ncy = (pl->desc.ny + G::CH - 1) / G::CH;
     P.nb = nb;
-    // level slabs: one CTA keeps its coefficient tiles for a whole slab; aim for >= 40 waves of CTAs (tail < 3 %)
+    // level slabs: one CTA keeps its coefficient tiles for a whole slab and pays its prologue (barrier set-up,
+    // coefficient staging, first un-overlapped tile load: ~8 us) once per slab, so slabs should be long; at least
+    // 16 waves of CTAs keep the tail below ~5 %.  (Measured: 8..80 waves are equivalent at nb = 62; short
+    // chunks of the host pipeline gain ~10 % from whole-batch slabs.)
     const int64_t ntiles = (int64_t)P.ncx * P.ncy;
-    static const long long waves = [] {  // tuning knob: minimum number of CTA waves (default 40)
+    static const long long waves = [] {  // tuning knob: minimum number of CTA waves (default 16)
         const char* e = getenv("GCMF_FUSED_WAVES");
         const long long v = e ? atoll(e) : 0;
-        return v > 0 ? v : 40LL;
+        return v > 0 ? v : 16LL;
     }();
     int64_t groups = (waves * pl->sm_count + ntiles - 1) / ntiles;
     if (groups < 1) groups = 1;
