@@ -15,6 +15,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -779,17 +780,18 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
     P.ncx = (pl->desc.nx + G::CW - 1) / G::CW;
     P.ncy = (pl->desc.ny + G::CH - 1) / G::CH;
     P.nb = nb;
-    // level slabs: one CTA keeps its coefficient tiles for a whole slab and pays its prologue (barrier set-up,
-    // coefficient staging, first un-overlapped tile load: ~8 us) once per slab, so slabs should be long; at least
-    // 16 waves of CTAs keep the tail below ~5 %.  (Measured: 8..80 waves are equivalent at nb = 62; short
-    // chunks of the host pipeline gain ~10 % from whole-batch slabs.)
+    // Level slabs.  One CTA keeps its coefficient tiles for a whole slab of levels and pays its prologue (barrier
+    // set-up, coefficient staging, the first un-overlapped tile load: about the cost of one level, c = 1) once per
+    // slab, so slabs should be long; but with dynamic CTA dispatch the tail of the launch is about one CTA
+    // duration, so they should not be too long either.  time ~ ntiles*(nb + g*c)/SMs + (nb/g + c) is minimal at
+    // g = sqrt(nb*SMs / (ntiles*c)) slabs per tile.  (Measured on cfg3: 1 slab 10.7 ms, 2 slabs 10.4 ms per launch at
+    // nb = 62; chunks of 7 levels from the host pipeline want a single slab.)  GCMF_FUSED_GROUPS overrides.
     const int64_t ntiles = (int64_t)P.ncx * P.ncy;
-    static const long long waves = [] {  // tuning knob: minimum number of CTA waves (default 16)
-        const char* e = getenv("GCMF_FUSED_WAVES");
-        const long long v = e ? atoll(e) : 0;
-        return v > 0 ? v : 16LL;
-    }();
-    int64_t groups = (waves * pl->sm_count + ntiles - 1) / ntiles;
+    int64_t groups = (int64_t)(sqrt((double)nb * pl->sm_count / (double)ntiles) + 0.5);
+    if (const char* e = getenv("GCMF_FUSED_GROUPS")) {
+        const long long v = atoll(e);
+        if (v > 0) groups = v;
+    }
     if (groups < 1) groups = 1;
     if (groups > nb) groups = nb;
     P.levels_per_cta = (int32_t)((nb + groups - 1) / groups);
