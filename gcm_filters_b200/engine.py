@@ -113,6 +113,19 @@ class DevicePlan:
 
 _ws_lock = threading.Lock()
 _workspaces = {}
+_launch_locks = {}
+
+
+def launch_lock(device_index):
+    """One launch sequence at a time per device: a filter call is a series of kernel launches that share the
+    device workspace and the plan's filter state, so calls from different host threads (e.g. dask's threaded
+    scheduler running one block per thread) must not interleave their launches.  Only the (short) host-side
+    launch sequence is serialised; the kernels themselves run asynchronously."""
+    with _ws_lock:
+        lock = _launch_locks.get(device_index)
+        if lock is None:
+            lock = _launch_locks[device_index] = threading.RLock()
+        return lock
 
 
 def workspace(device, nbytes):
@@ -242,7 +255,7 @@ def run_laplacian(lap, fields):
 # the filter of chunk i and the D2H copy of chunk i-1 overlap (three streams, event-chained).  Copies are
 # truly asynchronous only from / to pinned memory (torch CPU tensors with pin_memory, or `out=` pinned).
 PIPELINE_MIN_CHUNKS = 4
-PIPELINE_TARGET_CHUNKS = 8
+PIPELINE_TARGET_CHUNKS = int(__import__("os").environ.get("GCMF_PIPELINE_CHUNKS", "8"))
 PIPELINE_MAX_CHUNK_BYTES = 1 << 30
 _pipe_lock = threading.Lock()
 _pipe_state = {}
@@ -306,7 +319,6 @@ def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
             raise ValueError(f"`out` must have dtype {tdt}")
     chunk = _pipeline_chunk(nb, ny * nx * np_dtype.itemsize)
     plan = device_plan(lap, device.index, np_dtype, ny, nx)
-    plan.set_filter(p, c)
     nbuf = 2
     key = (device.index, str(tdt), ncomp, chunk, ny, nx)
     with _pipe_lock:
@@ -320,6 +332,15 @@ def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
             }
     din, dout, s_h2d, s_d2h = stt["din"], stt["dout"], stt["h2d"], stt["d2h"]
     s_comp = torch.cuda.current_stream(device)
+    with launch_lock(device.index):
+        plan.set_filter(p, c)
+        return _pipeline_loop(plan, stt, host_in, host_out, results, chunk, nb, ncomp, tdt, device, s_comp)
+
+
+def _pipeline_loop(plan, stt, host_in, host_out, results, chunk, nb, ncomp, tdt, device, s_comp):
+    torch = _torch()
+    nbuf = 2
+    din, dout, s_h2d, s_d2h = stt["din"], stt["dout"], stt["h2d"], stt["d2h"]
     ws = workspace(device, plan.lib.workspace_bytes(plan.handle, chunk))
     ev_h2d = [torch.cuda.Event() for _ in range(nbuf)]
     ev_comp = [torch.cuda.Event() for _ in range(nbuf)]
@@ -389,11 +410,10 @@ def run_filter(lap, p, c, fields, out=None):
     st = _Staged(lap, fields)
     plan = device_plan(lap, st.device.index, st.np_dtype, st.ny, st.nx)
     plan.check_batch(st.batch_shape)
-    plan.set_filter(p, c)
     outs = st.out_like()
-    nbytes = plan.lib.workspace_bytes(plan.handle, st.nb)
-    ws = workspace(st.device, nbytes)
-    with torch.cuda.device(st.device):
+    with launch_lock(st.device.index), torch.cuda.device(st.device):
+        plan.set_filter(p, c)
+        ws = workspace(st.device, plan.lib.workspace_bytes(plan.handle, st.nb))
         stream = torch.cuda.current_stream(st.device).cuda_stream
         plan.lib.filter(plan.handle, st.nb, _specs(st.dev), _specs(outs), ws.data_ptr(), ws.numel(), stream)
     return st.deliver(outs, out)
@@ -407,9 +427,9 @@ def filter_device(lap, p, c, dev_in, dev_out):
     nb, ny, nx = (int(s) for s in t0.shape)
     np_dtype = np.dtype(np.float32 if t0.dtype == torch.float32 else np.float64)
     plan = device_plan(lap, t0.device.index, np_dtype, ny, nx)
-    plan.set_filter(p, c)
-    nbytes = plan.lib.workspace_bytes(plan.handle, nb)
-    ws = workspace(t0.device, nbytes)
-    stream = torch.cuda.current_stream(t0.device).cuda_stream
-    plan.lib.filter(plan.handle, nb, _specs(dev_in), _specs(dev_out), ws.data_ptr(), ws.numel(), stream)
+    with launch_lock(t0.device.index):
+        plan.set_filter(p, c)
+        ws = workspace(t0.device, plan.lib.workspace_bytes(plan.handle, nb))
+        stream = torch.cuda.current_stream(t0.device).cuda_stream
+        plan.lib.filter(plan.handle, nb, _specs(dev_in), _specs(dev_out), ws.data_ptr(), ws.numel(), stream)
     return dev_out

@@ -410,3 +410,18 @@ def test_fused_level_slabs(g, dtype, levels, monkeypatch):
         assert np.array_equal(np.isnan(fused), np.isnan(plain)) and rel_l2(fused, plain) < 1e-14
     else:
         assert np.array_equal(fused, plain, equal_nan=True)
+
+
+def test_concurrent_calls_from_host_threads():
+    """dask's threaded scheduler calls filter_func from several host threads (one block each): the launch
+    sequences share the device workspace and must not interleave."""
+    from concurrent.futures import ThreadPoolExecutor
+    (f,), gv = fixtures.fixture("IRREGULAR_WITH_LAND", (96, 264))
+    flt = make_filter("IRREGULAR_WITH_LAND", gv, filter_scale=10.0, dx_min=1.0)
+    rng = np.random.default_rng(12)
+    blocks = [f[None] * (1 + 0.2 * rng.standard_normal((3, 1, 1))) for _ in range(8)]
+    serial = [flt.apply(b, None) for b in blocks]
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        threaded = list(pool.map(lambda b: flt.apply(b, None), blocks * 3))
+    for k, out in enumerate(threaded):
+        assert np.array_equal(out, serial[k % len(blocks)], equal_nan=True)
