@@ -319,7 +319,8 @@ def gpu_arm(args):
             while i <= n_steps:
                 kk = min(n_steps - i + 1, kfuse)
                 O1, O2 = bufs[2 * cur], bufs[2 * cur + 1]
-                timed("fused", kk, lambda: lib.cheb_fused(plan.handle, nb, i, kk, T1, T2, O1, O2, outs, sptr))
+                kind = "fused_first" if i == 1 else ("fused_last" if i + kk - 1 == n_steps else "fused")
+                timed(kind, kk, lambda: lib.cheb_fused(plan.handle, nb, i, kk, T1, T2, O1, O2, outs, sptr))
                 T1, T2 = O1, O2
                 cur ^= 1
                 i += kk
@@ -342,7 +343,8 @@ def gpu_arm(args):
     peak, peak_src = measured_hbm_peak()
     # algorithmic bytes of one launch = B_alg per grid-point step x points x steps the launch performs
     achieved = b_alg * nb * ny * nx * dom[1] / (dom_ms * 1e-3) / 1e9
-    kname = {"fused": f"fused_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)",
+    fk = f"fused_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)"
+    kname = {"fused": fk, "fused_first": fk + ", first block", "fused_last": fk + ", last block",
              "mid": "step_kernel<MODE_MID> (one Chebyshev step)", "first": "step_kernel<MODE_FIRST>",
              "last": "step_kernel<MODE_LAST>"}[dom[0]]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -354,7 +356,7 @@ def gpu_arm(args):
         try:
             with open(prof) as fh:
                 tr = json.load(fh)
-            key = args.workload if dom[0] == "fused" else args.workload + "_onestep"
+            key = args.workload if dom[0].startswith("fused") else args.workload + "_onestep"
             if key in tr:
                 roofline["traffic"] = tr[key]["bytes_per_pt_step"] * nb * ny * nx * dom[1]
                 roofline["traffic_source"] = tr[key]["source"]

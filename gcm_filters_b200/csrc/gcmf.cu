@@ -690,7 +690,7 @@ static int fused_kind(const gcmf_plan* p) {
 static bool fused_eligible(const gcmf_plan* p) { return fused_kind(p) >= 0; }
 
 #ifdef GCMF_HOSTEMU
-template <typename T, int KIND, bool EDGE> static void fused_host_t(const FusedParams<T>& P, int ncta) {
+template <typename T, int KIND, int EDGE> static void fused_host_t(const FusedParams<T>& P, int ncta) {
     using G = FusedGeom<T, FusedSplit<KIND>::value>;
     std::vector<T> smem((size_t)G::ntiles(KIND) * G::PLANE);
     std::vector<typename FusedTile<T, KIND, EDGE>::Thread> st(G::NTHREADS);
@@ -718,11 +718,15 @@ template <typename T, int KIND, bool EDGE> static void fused_host_t(const FusedP
     }
 }
 template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, int ncta) {
-    if (P.first || P.last) fused_host_t<T, KIND, true>(P, ncta);
-    else fused_host_t<T, KIND, false>(P, ncta);
+    switch ((P.first ? 1 : 0) | (P.last ? 2 : 0)) {
+        case 0: fused_host_t<T, KIND, 0>(P, ncta); break;
+        case 1: fused_host_t<T, KIND, 1>(P, ncta); break;
+        case 2: fused_host_t<T, KIND, 2>(P, ncta); break;
+        default: fused_host_t<T, KIND, 3>(P, ncta); break;
+    }
 }
 #else
-template <typename T, int KIND, bool EDGE>
+template <typename T, int KIND, int EDGE>
 static int launch_fused_kernel_t(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
     using G = FusedGeom<T, FusedSplit<KIND>::value>;
     static bool attr_done = false;
@@ -737,8 +741,12 @@ static int launch_fused_kernel_t(const FusedParams<T>& P, int64_t ncta, cudaStre
     return GCMF_OK;
 }
 template <typename T, int KIND> static int launch_fused_kernel(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
-    if (P.first || P.last) return launch_fused_kernel_t<T, KIND, true>(P, ncta, st);
-    return launch_fused_kernel_t<T, KIND, false>(P, ncta, st);
+    switch ((P.first ? 1 : 0) | (P.last ? 2 : 0)) {
+        case 0: return launch_fused_kernel_t<T, KIND, 0>(P, ncta, st);
+        case 1: return launch_fused_kernel_t<T, KIND, 1>(P, ncta, st);
+        case 2: return launch_fused_kernel_t<T, KIND, 2>(P, ncta, st);
+    }
+    return launch_fused_kernel_t<T, KIND, 3>(P, ncta, st);
 }
 #endif
 

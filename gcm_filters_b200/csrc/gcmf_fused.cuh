@@ -146,8 +146,9 @@ GCMF_HD void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
 #endif
 }
 
-// EDGE = false: a block strictly inside the recurrence (P.first and P.last are known to be 0 at compile time)
-template <typename T, int KIND, bool EDGE> struct FusedTile {
+// EDGE: which ends of the recurrence the block touches, known at compile time so that the common mid block
+// carries none of it: bit 0 = the block starts at step 1 (P.first), bit 1 = it ends at step n_steps (P.last).
+template <typename T, int KIND, int EDGE> struct FusedTile {
     static constexpr int XS = FusedSplit<KIND>::value;
     using G = FusedGeom<T, XS>;
     using Thread = FusedThread<T, XS>;
@@ -156,8 +157,8 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
     int cy0, cx0;      // global coordinates of the first core element
     T* smem;
     bool masked;       // REG5 with a wet mask (nan_to_num + mask), else raw values (NaNs spread)
-    GCMF_HD bool is_first() const { return EDGE && P.first; }
-    GCMF_HD bool is_last() const { return EDGE && P.last; }
+    static GCMF_HD constexpr bool is_first() { return (EDGE & 1) != 0; }
+    static GCMF_HD constexpr bool is_last() { return (EDGE & 2) != 0; }
 
     GCMF_HD FusedTile(const FusedParams<T>& P_, int tile, T* smem_) : P(P_), smem(smem_) {
         const int cx = tile % P.ncx, cy = tile / P.ncx;
@@ -481,7 +482,7 @@ template <typename T, int KIND, bool EDGE> struct FusedTile {
 };
 
 #ifdef __CUDACC__
-template <typename T, int KIND, bool EDGE>
+template <typename T, int KIND, int EDGE>
 __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREADS, 1)
     fused_kernel(const __grid_constant__ FusedParams<T> P) {
     using G = FusedGeom<T, FusedSplit<KIND>::value>;
