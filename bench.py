@@ -404,8 +404,10 @@ def banded_arm(args):
     fa["filter_shape"] = FilterShape[fa["filter_shape"]]
     flt = Filter(grid_type=GridType[cfg["grid_type"]], grid_vars=cfg["grid_vars"], **fa)
     n_steps = int(flt.n_steps)
-    cls = FusedBandedFilter if args.fused else (PeerBandedFilter if args.peer else BandedFilter)
-    bf = cls(flt, rank, world)
+    if args.fused:
+        bf = FusedBandedFilter(flt, rank, world, exchange="peer" if args.peer else "nccl")
+    else:
+        bf = (PeerBandedFilter if args.peer else BandedFilter)(flt, rank, world)
     st = bf.stage(*cfg["fields"])
     f0 = cfg["fields"][0]
     ny, nx = f0.shape[-2:]
@@ -459,7 +461,8 @@ def banded_arm(args):
         "dtype": "f64" if w == 8 else "f32", "data": "synthetic (numpy PCG64, SURVEY 8(d))",
         "config": dict(workload_descr(cfg, n_steps),
                        sharding=f"{world} latitude band(s), " +
-                       ("4 ghost rows, fused 4-step blocks, one NCCL exchange per block" if args.fused else
+                       ("4 ghost rows, fused 4-step blocks, ghost rows pulled from peer memory once per block" if args.fused and args.peer
+                        else "4 ghost rows, fused 4-step blocks, one NCCL exchange per block" if args.fused else
                         "ghost rows stored by the step kernels into the neighbours' peer memory (NVLink), flag-synchronised"
                         if args.peer else "NCCL send/recv per Chebyshev step")),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -414,7 +414,26 @@ class FusedBandedFilter(BandedFilter):
     runs up to four Chebyshev steps per launch (``gcmf_cheb_fused`` on a band plan) and exchanges the ghost
     rows of ``T_{i+k-1}`` and ``T_{i+k-2}`` **once per block** instead of once per step (north_star item 3:
     "per-step-block halo exchange").  Scalar FLUX / REGULAR5 operators on doubly periodic grids; the band must
-    be at least one tile high (32 rows) and ``nx`` a multiple of the vector width."""
+    be at least one tile high (32 rows) and ``nx`` a multiple of the vector width.
+
+    ``exchange="nccl"``: pack, grouped NCCL send/recv, unpack.  ``exchange="peer"``: the ghosted arrays live in
+    symmetric memory; after a device-side barrier every rank *pulls* its ghost rows straight out of its
+    neighbours' arrays over NVLink (four strided copies per block, no NCCL, no packing).  Two buffer pairs
+    ping-pong between blocks, so one barrier per block also covers the write-after-read hazards.
+    """
+
+    def __init__(self, flt, rank, world, group=None, library=None, device=None, exchange="nccl"):
+        super().__init__(flt, rank, world, group=group, library=library, device=device)
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        self.exchange = exchange if self.world > 1 else "nccl"
+        self._symm = None
+
+    def close(self):
+        import gc
+
+        self._symm = None
+        gc.collect()
 
     def _fused_plan(self, np_dtype, ny, nx):
         flags_all = self.lap._planes.flags
@@ -439,45 +458,77 @@ class FusedBandedFilter(BandedFilter):
         nyl = j1 - j0
         nb = int(np.prod(f0.shape[:-2])) if f0.ndim > 2 else 1
         tdt = torch.float32 if np_dtype == np.float32 else torch.float64
+        bands = band_rows(ny, self.world)
+        rows = max(b - a for a, b in bands) + 2 * H  # common allocation so that every rank has the same layout
+        peers = None
+        if self.exchange == "peer":
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
 
-        def new():
-            return torch.zeros((1, nb, nyl + 2 * H, nx), dtype=tdt, device=self.device)
-
+            n_arrays, slab = 6, nb * rows * nx
+            if self._symm is None or self._symm[0] != (tdt, slab):
+                buf = symm_mem.empty(n_arrays * slab, dtype=tdt, device=self.device)
+                hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                self._symm = ((tdt, slab), buf, hdl)
+            _, buf, hdl = self._symm
+            buf.zero_()
+            arrays = [buf[k * slab:(k + 1) * slab].view(1, nb, rows, nx) for k in range(n_arrays)]
+            north, south = (self.rank + 1) % self.world, (self.rank - 1) % self.world
+            peers = dict(hdl=hdl, nyl_south=bands[south][1] - bands[south][0],
+                         north=[hdl.get_buffer(north, (1, nb, rows, nx), tdt, k * slab) for k in range(n_arrays)],
+                         south=[hdl.get_buffer(south, (1, nb, rows, nx), tdt, k * slab) for k in range(n_arrays)])
+        else:
+            arrays = [torch.zeros((1, nb, rows, nx), dtype=tdt, device=self.device) for _ in range(6)]
         X0 = torch.as_tensor(np.ascontiguousarray(f0.reshape((nb, ny, nx))[:, j0:j1])).to(device=self.device, dtype=tdt)
-        return dict(h=h, flags=flags, j0=j0, j1=j1, nyl=nyl, nb=nb, nx=nx, ncomp=1, H=H, X0=X0, X=new(),
-                    pairs=[[new(), new()], [new(), new()]], P=new(),
-                    bar=torch.empty((1, nb, nyl, nx), dtype=tdt, device=self.device), batch_shape=f0.shape[:-2])
+        return dict(h=h, flags=flags, j0=j0, j1=j1, nyl=nyl, nb=nb, nx=nx, ncomp=1, H=H, rows=rows, X0=X0, arrays=arrays,
+                    peers=peers, bar=torch.empty((1, nb, nyl, nx), dtype=tdt, device=self.device),
+                    batch_shape=f0.shape[:-2])
+
+    def _exchange_ghosts(self, st, idxs):
+        """Fill the H ghost rows on both sides of the arrays `idxs` (owned rows sit at [H, H+nyl))."""
+        H, nyl = st["H"], st["nyl"]
+        if st["peers"] is None:
+            for k in idxs:  # NCCL send/recv on the rows actually in use
+                self._exchange(st["arrays"][k][..., :nyl + 2 * H, :], True, H)
+            return
+        pr = st["peers"]
+        pr["hdl"].barrier(channel=0)  # every rank has finished writing its owned rows (and reading old ghosts)
+        ns = pr["nyl_south"]
+        for k in idxs:
+            mine = st["arrays"][k]
+            mine[..., 0:H, :].copy_(pr["south"][k][..., ns:ns + H, :])                    # its top owned rows
+            mine[..., H + nyl:2 * H + nyl, :].copy_(pr["north"][k][..., H:2 * H, :])      # its bottom owned rows
 
     def run(self, st):
         import torch
 
         lib = self.lib
-        h, flags, nyl, nb, nx, H = st["h"], st["flags"], st["nyl"], st["nb"], st["nx"], st["H"]
+        h, flags, nyl, nb, nx, H, rows = st["h"], st["flags"], st["nyl"], st["nb"], st["nx"], st["H"], st["rows"]
         n = int(self.spec.n_steps)
-        X, bar = st["X"], st["bar"]
-        es = X.element_size()
-        rows = nyl + 2 * H
+        A, bar = st["arrays"], st["bar"]
+        es = A[0].element_size()
 
-        def inner(t):  # the owned rows start H rows into the ghosted array
-            return [(t[0].data_ptr() + H * nx * es, nx, rows * nx)]
+        def inner(k):  # the owned rows start H rows into the ghosted array
+            return [(A[k][0].data_ptr() + H * nx * es, nx, rows * nx)]
 
         plain = [(bar[0].data_ptr(), nx, nyl * nx)]
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
-        X[0, :, H:H + nyl].copy_(st["X0"])
+        x = 0
+        A[0][0, :, H:H + nyl].copy_(st["X0"])
         if flags & _AREA_FLAG:  # x = f * area on the owned rows (kernels.py:100-101), then its ghosts
-            lib.prepare(h, nb, inner(X), inner(st["P"]), stream)
-            X = st["P"]
-        self._exchange(X, True, H)
-        T1 = T2 = X
+            lib.prepare(h, nb, inner(0), inner(1), stream)
+            x = 1
+        self._exchange_ghosts(st, [x])
+        pairs = [(2, 3), (4, 5)]
+        t1 = t2 = x
         cur, i = 0, 1
         while i <= n:
             kk = min(H, n - i + 1)
-            O1, O2 = st["pairs"][cur]
-            lib.cheb_fused(h, nb, i, kk, inner(T1), inner(T2), inner(O1), inner(O2), plain, stream)
+            o1, o2 = pairs[cur]
+            lib.cheb_fused(h, nb, i, kk, inner(t1), inner(t2), inner(o1), inner(o2), plain, stream)
             if i + kk <= n:  # the next block reads the ghost rows of both carried fields
-                self._exchange(O1, True, H)
-                self._exchange(O2, True, H)
-            T1, T2 = O1, O2
+                self._exchange_ghosts(st, [o1, o2])
+            t1, t2 = o1, o2
             cur ^= 1
             i += kk
         return bar

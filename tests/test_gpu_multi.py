@@ -60,8 +60,12 @@ def _worker(rank, world, port, g, shape, q):
                                                    for o, s in zip(pouts, single))
         pbf.close()
         if g == "IRREGULAR_WITH_LAND":  # temporal blocking on bands: 4 ghost rows, one NCCL exchange per block
-            fouts, (fj0, fj1) = FusedBandedFilter(flt, rank, world).apply(*fields)
-            ok = ok and (fj0, fj1) == (j0, j1) and np.array_equal(fouts[0], single[0][..., j0:j1, :], equal_nan=True)
+            for exch in ("nccl", "peer"):
+                fbf = FusedBandedFilter(flt, rank, world, exchange=exch)
+                for _ in range(2):
+                    fouts, (fj0, fj1) = fbf.apply(*fields)
+                ok = ok and (fj0, fj1) == (j0, j1) and np.array_equal(fouts[0], single[0][..., j0:j1, :], equal_nan=True)
+                fbf.close()
         # batch sharding with an all-gather of the slabs
         full = (apply_batch_sharded(lambda a: flt.apply(a, None), fields[0], rank, world, gather=True)
                 if len(fields) == 1 else None)
