@@ -19,7 +19,7 @@ EXPORTS = [
     "gcmf_version", "gcmf_sm_arch", "gcmf_last_error", "gcmf_plan_create", "gcmf_plan_destroy",
     "gcmf_plan_set_plane", "gcmf_plan_set_filter", "gcmf_workspace_bytes", "gcmf_laplacian", "gcmf_filter",
     "gcmf_cheb_step", "gcmf_prepare", "gcmf_launch_count", "gcmf_fused_max_steps", "gcmf_plan_set_steps_per_block",
-    "gcmf_cheb_fused", "gcmf_cheb_step_halo", "gcmf_halo_push",
+    "gcmf_cheb_fused", "gcmf_cheb_step_halo", "gcmf_halo_push", "gcmf_finalize",
 ]
 
 
@@ -68,6 +68,8 @@ class Library:
         lib.gcmf_workspace_bytes.argtypes = [vp, i64, ctypes.POINTER(ctypes.c_size_t)]
         lib.gcmf_laplacian.argtypes = [vp, i64, fp, fp, vp]
         lib.gcmf_prepare.argtypes = [vp, i64, fp, fp, vp]
+        lib.gcmf_finalize.argtypes = [vp, i64, fp, fp, vp]
+        lib.gcmf_finalize.restype = ctypes.c_int
         lib.gcmf_filter.argtypes = [vp, i64, fp, fp, vp, ctypes.c_size_t, vp]
         lib.gcmf_cheb_step.argtypes = [vp, i64, i32, fp, fp, fp, fp, vp]
         lib.gcmf_fused_max_steps.argtypes = [vp]
@@ -127,6 +129,9 @@ class Library:
 
     def prepare(self, h, nb, fin, fout, stream=0):
         self.check(self.lib.gcmf_prepare(h, nb, self.fields(fin), self.fields(fout), ctypes.c_void_p(stream)))
+
+    def finalize(self, h, nb, fin, fout, stream=0):
+        self.check(self.lib.gcmf_finalize(h, nb, self.fields(fin), self.fields(fout), ctypes.c_void_p(stream)))
 
     def filter(self, h, nb, fin, fout, ws_ptr, ws_bytes, stream=0):
         self.check(self.lib.gcmf_filter(h, nb, self.fields(fin), self.fields(fout), ctypes.c_void_p(ws_ptr),

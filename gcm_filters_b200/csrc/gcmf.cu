@@ -296,14 +296,14 @@ __global__ void halo_push_kernel(FieldRef<const T> f0, FieldRef<const T> f1, int
 
 template <typename T>
 __global__ void prepare_kernel(const T* in, int64_t in_pitch, int64_t in_bs, T* out, int64_t out_pitch, int64_t out_bs,
-                               PlaneRef area, int ny, int nx, int64_t nb) {
+                               PlaneRef area, int ny, int nx, int64_t nb, bool divide) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i >= nx) return;
     for (int64_t b = blockIdx.z; b < nb; b += gridDim.z) {
         const T* a = plane_base<T>(area, (int)b);
         prepare_body<T>(in, out, a, b * in_bs + (int64_t)j * in_pitch + i, b * out_bs + (int64_t)j * out_pitch + i,
-                        (int64_t)j * area.pitch + i);
+                        (int64_t)j * area.pitch + i, divide);
     }
 }
 
@@ -532,7 +532,16 @@ extern "C" int gcmf_laplacian(gcmf_plan* p, int64_t nb, const gcmf_field* in, co
     return run_step(p, nb, MODE_LAP, in, nullptr, out, nullptr, 0.0, 0.0, (cudaStream_t)stream);
 }
 
+static int run_area_op(gcmf_plan* p, int64_t nb, const gcmf_field* in, const gcmf_field* out, bool divide, void* stream);
+
 extern "C" int gcmf_prepare(gcmf_plan* p, int64_t nb, const gcmf_field* in, const gcmf_field* out, void* stream) {
+    return run_area_op(p, nb, in, out, false, stream);
+}
+extern "C" int gcmf_finalize(gcmf_plan* p, int64_t nb, const gcmf_field* in, const gcmf_field* out, void* stream) {
+    return run_area_op(p, nb, in, out, true, stream);
+}
+
+static int run_area_op(gcmf_plan* p, int64_t nb, const gcmf_field* in, const gcmf_field* out, bool divide, void* stream) {
     if (!p || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
     TRY(check_fields(p, in, "in"));
     TRY(check_fields(p, out, "out"));
@@ -553,11 +562,11 @@ extern "C" int gcmf_prepare(gcmf_plan* p, int64_t nb, const gcmf_field* in, cons
                     } else if (p->desc.dtype == GCMF_F64) {
                         prepare_body<double>((const double*)in[k].ptr, (double*)out[k].ptr,
                                              plane_base<double>(p->plane[1], (int)b), ii, oi,
-                                             (int64_t)j * p->plane[1].pitch + i);
+                                             (int64_t)j * p->plane[1].pitch + i, divide);
                     } else {
                         prepare_body<float>((const float*)in[k].ptr, (float*)out[k].ptr,
                                             plane_base<float>(p->plane[1], (int)b), ii, oi,
-                                            (int64_t)j * p->plane[1].pitch + i);
+                                            (int64_t)j * p->plane[1].pitch + i, divide);
                     }
                 }
     if (p->desc.flags & GCMF_FLAG_AREA) gcmf_count_launch(p->ncomp);
@@ -576,11 +585,11 @@ extern "C" int gcmf_prepare(gcmf_plan* p, int64_t nb, const gcmf_field* in, cons
         if (p->desc.dtype == GCMF_F64)
             prepare_kernel<double><<<grd, blk, 0, st>>>((const double*)in[k].ptr, in[k].pitch, in[k].bstride,
                                                         (double*)out[k].ptr, out[k].pitch, out[k].bstride,
-                                                        p->plane[1], ny, nx, nb);
+                                                        p->plane[1], ny, nx, nb, divide);
         else
             prepare_kernel<float><<<grd, blk, 0, st>>>((const float*)in[k].ptr, in[k].pitch, in[k].bstride,
                                                        (float*)out[k].ptr, out[k].pitch, out[k].bstride, p->plane[1],
-                                                       ny, nx, nb);
+                                                       ny, nx, nb, divide);
         gcmf_count_launch(1);
         CUDA_TRY(cudaGetLastError());
     }

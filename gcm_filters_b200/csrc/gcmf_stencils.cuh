@@ -563,10 +563,11 @@ template <typename T> struct CgridTile {
     }
 };
 
-// prepare: x = f * area (kernels.py:100-101)
+// prepare: x = f * area (kernels.py:100-101); finalize: f = x / area (kernels.py:103-104)
 template <typename T>
-GCMF_HD void prepare_body(const T* in, T* out, const T* area, int64_t idx_in, int64_t idx_out, int64_t idx_area) {
-    out[idx_out] = in[idx_in] * area[idx_area];
+GCMF_HD void prepare_body(const T* in, T* out, const T* area, int64_t idx_in, int64_t idx_out, int64_t idx_area,
+                          bool divide = false) {
+    out[idx_out] = divide ? in[idx_in] / area[idx_area] : in[idx_in] * area[idx_area];
 }
 
 }  // namespace gcmf

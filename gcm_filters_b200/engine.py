@@ -35,18 +35,6 @@ def _is_torch(a):
     return hasattr(a, "detach") and hasattr(a, "device")
 
 
-def like(grid_var, field):
-    """grid variable as the same kind of array as `field` (numpy or torch on field's device)."""
-    if _is_torch(field):
-        import torch
-
-        g = grid_var if _is_torch(grid_var) else torch.as_tensor(np.asarray(grid_var))
-        return g.to(device=field.device, dtype=field.dtype)
-    if _is_torch(grid_var):
-        return grid_var.detach().cpu().numpy()
-    return np.asarray(getattr(grid_var, "values", grid_var))
-
-
 # ------------------------------------------------------------------------------------------
 # per-(operator, device, dtype, shape) device state
 # ------------------------------------------------------------------------------------------
@@ -399,6 +387,20 @@ def _wants_pipeline(lap, fields, out):
     if nb < PIPELINE_MIN_CHUNKS * _pipeline_chunk(nb, shape[-2] * shape[-1] * np_dtype.itemsize):
         return None
     return shape, np_dtype
+
+
+def run_area_op(lap, field, divide):
+    """AreaWeightedMixin.prepare (field * area) / finalize (field / area) on the GPU (kernels.py:100-104)."""
+    torch = _torch()
+    st = _Staged(lap, (field,))
+    plan = device_plan(lap, st.device.index, st.np_dtype, st.ny, st.nx)
+    plan.check_batch(st.batch_shape)
+    outs = st.out_like()
+    with launch_lock(st.device.index), torch.cuda.device(st.device):
+        stream = torch.cuda.current_stream(st.device).cuda_stream
+        op = plan.lib.finalize if divide else plan.lib.prepare
+        op(plan.handle, st.nb, _specs(st.dev), _specs(outs), stream)
+    return st.deliver(outs)[0]
 
 
 def run_filter(lap, p, c, fields, out=None):

@@ -175,13 +175,14 @@ class BaseVectorLaplacian(_BaseLaplacian):
 
 class AreaWeightedMixin:
     """Weight and de-weight a field by the cell area (kernels.py:89-104).  Inside the filter both
-    happen on the device (gcmf_prepare, last Chebyshev step); these methods serve direct callers."""
+    happen in the filter kernels; these methods serve direct callers of the operator protocol and run
+    on the device as well (gcmf_prepare / gcmf_finalize)."""
 
     def prepare(self, field):
-        return field * engine.like(self.area, field)
+        return engine.run_area_op(self, field, divide=False)
 
     def finalize(self, field):
-        return field / engine.like(self.area, field)
+        return engine.run_area_op(self, field, divide=True)
 
 
 # ---------------------------------------------------------------------------------------------

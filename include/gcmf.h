@@ -189,6 +189,9 @@ int gcmf_halo_push(gcmf_plan *plan, int64_t nb, const gcmf_field *field, const g
 /* x = field * area (AreaWeightedMixin.prepare, kernels.py:100-101); a copy when the plan has no
  * GCMF_FLAG_AREA.  gcmf_filter calls this itself. */
 int gcmf_prepare(gcmf_plan *plan, int64_t nb, const gcmf_field *in, const gcmf_field *out, void *stream);
+/* field = x / area (AreaWeightedMixin.finalize, kernels.py:103-104); a copy without GCMF_FLAG_AREA.  The filter
+ * entry points finalize by themselves; this serves direct callers of the operator protocol. */
+int gcmf_finalize(gcmf_plan *plan, int64_t nb, const gcmf_field *in, const gcmf_field *out, void *stream);
 
 /* Number of kernel launches issued through this library by the calling process so far
  * (bench.py reports it as gpu_launches). */

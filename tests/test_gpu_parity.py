@@ -425,3 +425,20 @@ def test_concurrent_calls_from_host_threads():
         threaded = list(pool.map(lambda b: flt.apply(b, None), blocks * 3))
     for k, out in enumerate(threaded):
         assert np.array_equal(out, serial[k % len(blocks)], equal_nan=True)
+
+
+def test_operator_protocol_prepare_call_finalize():
+    """prepare / __call__ / finalize of the area-weighted operators (reference kernels.py:89-104) run on the device."""
+    for g in ("REGULAR_AREA_WEIGHTED", "REGULAR_WITH_LAND_AREA_WEIGHTED", "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED"):
+        (f,), gv = fixtures.fixture(g, (48, 72))
+        lap = ALL_KERNELS[GridType[g]](**gv)
+        lib = _cabi.get_library()
+        n0 = lib.launch_count()
+        x = lap.prepare(f)
+        assert lib.launch_count() == n0 + 1 and np.array_equal(x, f * gv["area"])
+        assert np.array_equal(lap.finalize(x), (f * gv["area"]) / gv["area"])
+        op = np_oracle.make_operator(g, gv)
+        assert np.array_equal(lap(x), op.apply(op.prepare(f)))
+    (f,), gv = fixtures.fixture("REGULAR_WITH_LAND", (48, 72))
+    lap = ALL_KERNELS[GridType.REGULAR_WITH_LAND](**gv)
+    assert lap.prepare(f) is f and lap.finalize(f) is f  # identity for the other operators (kernels.py:47-54)
