@@ -16,7 +16,8 @@
 //     below and the W/E columns from the work tile;
 //   * the running filtered field `bar` stays in registers for the k steps; T_{i+k-1}, T_{i+k-2} and
 //     bar are written back from registers;
-//   * FLUX: the coefficient tiles (ce, cn, ra) are staged once per CTA and reused for every level;
+//   * FLUX: the coefficient tiles (ce, cn, ra) are staged once per CTA and reused for every level; warps
+//     synchronise with their neighbour warps only, through per-warp mbarriers (no CTA barrier per step);
 //     REGULAR5: the wet mask and wet_fac of the own points are packed into two registers once per CTA.
 // HBM traffic per grid-point step: (2*rho + 4) * w / k bytes instead of 5 * w  (rho = tile/core area).
 //
@@ -59,7 +60,7 @@ template <typename T, int XS = 1> struct FusedGeom {
     static constexpr int PLANE = TH * TW;           // elements per shared-memory tile (32 KiB)
     // tiles: X, Y (TMA landing of T1, T2), S0, S1 (sanitized ping-pong) [+ ce, cn, ra for FLUX]
     static GCMF_HD constexpr int ntiles(int kind) { return kind == FK_FLUX ? 7 : 4; }
-    static GCMF_HD constexpr size_t smem_bytes(int kind) { return (size_t)ntiles(kind) * PLANE * sizeof(T) + 256; }
+    static GCMF_HD constexpr size_t smem_bytes(int kind) { return (size_t)ntiles(kind) * PLANE * sizeof(T) + 1024; }
 };
 
 template <typename T> struct FusedParams {
@@ -103,6 +104,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* mb, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* mb, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mb)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* mb) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mb)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* mb, unsigned parity) {
     asm volatile(
         "{\n"
@@ -114,15 +118,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, unsigned parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(mb)), "r"(parity) : "memory");
 }
-// ---- warp-to-warp progress flags in shared memory (release / acquire at CTA scope) ----
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
+// ---- drain counter of the landing tiles (acquire-release at CTA scope) ----
 __device__ __forceinline__ uint32_t atom_add_acqrel_u32(uint32_t* p, uint32_t v) {
     uint32_t old;
     asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
@@ -503,7 +499,15 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
         mbar_init(&mb[1], G::TH);
         fence_mbar_init();
     }
-    if (tid < 40) reinterpret_cast<uint32_t*>(mb + 2)[tid] = 0u;  // progress flags [32] + drain counter
+    if (tid < G::NTHREADS / 32) {  // per-warp progress barriers: expected arrivals = number of neighbour warps
+        constexpr int WPR_ = G::NTX / 32;
+        const int wy_ = tid / WPR_, wx_ = tid % WPR_;
+        const unsigned cnt = (wx_ > 0) + (wx_ < WPR_ - 1) + (wy_ > 0) + (wy_ < G::NTY - 1);
+        mbar_init(&mb[2 + 2 * tid], cnt);
+        mbar_init(&mb[2 + 2 * tid + 1], cnt);
+    }
+    if (tid == 32) *reinterpret_cast<uint32_t*>(mb + 2 + 2 * 32) = 0u;  // drain counter
+    if (tid < 32) fence_mbar_init();
     static_assert(G::TH <= 32 && G::R >= G::H, "one refill lane per tile row; inner threads own only in-region rows");
     __syncthreads();
     if (tid < G::TH) {
@@ -545,29 +549,29 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
     // rows those same warps read in phase g-1.  Both hazards are covered by one rule: start phase g only
     // when these (up to four) neighbour warps have completed phase g-1.  Warps therefore drift apart by up to one phase per
     // hop, which spreads shared-memory and fp64 work in time instead of convoying at a barrier.
-    uint32_t* prog = reinterpret_cast<uint32_t*>(mb + 2);  // [NWARPS] completed-phase counters
-    uint32_t* xcount = prog + 32;                           // warps that have drained the landing tiles
+    // Progress is signalled through mbarriers rather than polled flags: a warp that has completed phase g
+    // arrives (release) on barrier [g & 1] of each neighbour; a warp about to start phase g+1 waits (acquire, the
+    // hardware parks it: no polling instructions) on its own barrier [g & 1], whose expected arrival count is its
+    // number of neighbours.  Two barriers per warp suffice because a neighbour can complete phase g+2 only after
+    // this warp has completed g+1, i.e. after it has consumed phase g of the same barrier.
+    uint64_t* nbar = mb + 2;                                          // [NWARPS][2]
+    uint32_t* xcount = reinterpret_cast<uint32_t*>(mb + 2 + 2 * 32);  // warps that have drained the landing tiles
     constexpr int NWARPS = G::NTHREADS / 32;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int WPR = G::NTX / 32;  // warps per row group
     const int wy = warp / WPR, wx = warp % WPR;
-    int nb_warp = -1;  // lanes 0..3 each watch one neighbour warp (west, east, south, north)
+    int nb_warp = -1;  // lanes 0..3 each serve one neighbour warp (west, east, south, north)
     if (lane == 0 && wx > 0) nb_warp = warp - 1;
     if (lane == 1 && wx < WPR - 1) nb_warp = warp + 1;
     if (lane == 2 && wy > 0) nb_warp = warp - WPR;
     if (lane == 3 && wy < G::NTY - 1) nb_warp = warp + WPR;
-    auto wait_neighbours = [&](uint32_t need) {
+    auto wait_neighbours = [&](uint32_t need) {  // all neighbours have completed phase `need`
         if (need == 0) return;
-        unsigned spins = 0;
-        while (true) {
-            const bool ok = nb_warp < 0 || ld_acquire_u32(&prog[nb_warp]) >= need;
-            if (__all_sync(0xffffffffu, ok)) break;
-            if (++spins > (1u << 28)) asm volatile("trap;");  // a lost wake-up must not hang the GPU
-        }
+        mbar_wait(&nbar[warp * 2 + (need & 1u)], ((need - 1u) >> 1) & 1u);
     };
-    auto publish = [&](uint32_t done) {
+    auto publish = [&](uint32_t done) {  // this warp has completed phase `done`
         __syncwarp();
-        if (lane == 0) st_release_u32(&prog[warp], done);
+        if (nb_warp >= 0) mbar_arrive(&nbar[nb_warp * 2 + (done & 1u)]);
     };
     int it = 0;
     for (int64_t l = l0; l < l1; ++l, ++it) {

@@ -333,8 +333,8 @@ def test_pipelined_host_path_matches_monolithic():
 
 
 def test_fused_neighbour_sync_is_deterministic():
-    """The flux kernel replaces the CTA barrier by release/acquire progress flags between neighbouring warps
-    (compute-sanitizer racecheck only models barriers and cannot see them).  A missing dependency would show
+    """The flux kernel replaces the CTA barrier by per-warp mbarriers between neighbouring warps
+    (compute-sanitizer racecheck only models CTA barriers).  A missing dependency would show
     up as run-to-run differences: 25 repetitions must agree bit for bit with each other and with the
     barrier-free one-step kernels."""
     import torch
