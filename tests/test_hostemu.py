@@ -107,3 +107,41 @@ def test_batched_planes():
     ref = np_oracle.laplacian("REGULAR_WITH_LAND", {"wet_mask": mask}, f)
     (got,) = EmuPlan(lap, np.float64, *shape).laplacian((f,))
     assert np.array_equal(got, ref)
+
+
+def test_c_abi_argument_checks():
+    """Error paths of the C ABI (same code in libgcmf.so): status code + message, nothing is launched."""
+    from gcm_filters_b200 import _cabi
+    from hostemu_util import emu_library
+    lib = emu_library()
+    (f,), gv = fixtures.fixture("IRREGULAR_WITH_LAND", (40, 136))
+    lap = ALL_KERNELS[GridType.IRREGULAR_WITH_LAND](**gv)
+    plan = EmuPlan(lap, np.float64, 40, 136)
+    x = np.ascontiguousarray(f)[None].copy()
+    y = np.zeros_like(x)
+    spec = [(x.ctypes.data, 136, 40 * 136)]
+    out = [(y.ctypes.data, 136, 40 * 136)]
+    with pytest.raises(_cabi.GcmfError, match="gcmf_plan_set_filter has not been called"):
+        lib.filter(plan.h, 1, spec, out, 0, 0)
+    lib.plan_set_filter(plan.h, [0.5, 0.3, 0.1, 0.05], 0.25)
+    with pytest.raises(_cabi.GcmfError, match="workspace too small"):
+        lib.filter(plan.h, 1, spec, out, 0, 0)
+    ws = np.zeros(lib.workspace_bytes(plan.h, 1) + 256, dtype=np.uint8)
+    base = ws.ctypes.data + (-ws.ctypes.data) % 256
+    with pytest.raises(_cabi.GcmfError, match="must not alias"):
+        lib.filter(plan.h, 1, spec, spec, base, ws.size - 256)
+    with pytest.raises(_cabi.GcmfError, match="outside 1"):
+        lib.cheb_step(plan.h, 1, 9, spec, spec, out, out)
+    with pytest.raises(_cabi.GcmfError, match="must lie inside"):
+        lib.cheb_fused(plan.h, 1, 2, 4, spec, spec, out, out, out)
+    with pytest.raises(_cabi.GcmfError, match="n_steps must be >= 2"):
+        lib.plan_set_filter(plan.h, [1.0, 0.5], 0.25)
+    with pytest.raises(_cabi.GcmfError, match="steps_per_block"):
+        lib.set_steps_per_block(plan.h, 9)
+    with pytest.raises(_cabi.GcmfError, match="grid .* too small"):
+        lib.plan_create(_cabi.OP_FLUX, _cabi.GCMF_F64, 0, 8, _cabi.FLAG_WRAP_Y, 0)
+    band = lib.plan_create(_cabi.OP_REGULAR5, _cabi.GCMF_F64, 40, 136, 0, 0)  # no WRAP_Y: a latitude band
+    lib.plan_set_filter(band, [0.5, 0.3, 0.1, 0.05], 0.25)
+    with pytest.raises(_cabi.GcmfError, match="latitude band"):
+        lib.filter(band, 1, spec, out, base, ws.size - 256)
+    lib.plan_destroy(band)
