@@ -245,6 +245,7 @@ def run_laplacian(lap, fields):
 PIPELINE_MIN_CHUNKS = 4
 PIPELINE_TARGET_CHUNKS = int(__import__("os").environ.get("GCMF_PIPELINE_CHUNKS", "8"))
 PIPELINE_MAX_CHUNK_BYTES = 1 << 30
+PIPELINE_NBUF = 2  # device-side input / output chunk buffers in flight
 _pipe_lock = threading.Lock()
 _pipe_state = {}
 
@@ -307,8 +308,8 @@ def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
             raise ValueError(f"`out` must have dtype {tdt}")
     chunk = _pipeline_chunk(nb, ny * nx * np_dtype.itemsize)
     plan = device_plan(lap, device.index, np_dtype, ny, nx)
-    nbuf = 2
-    key = (device.index, str(tdt), ncomp, chunk, ny, nx)
+    nbuf = PIPELINE_NBUF
+    key = (device.index, str(tdt), ncomp, chunk, ny, nx, nbuf)
     with _pipe_lock:
         stt = _pipe_state.get(key)
         if stt is None:
@@ -327,7 +328,7 @@ def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
 
 def _pipeline_loop(plan, stt, host_in, host_out, results, chunk, nb, ncomp, tdt, device, s_comp):
     torch = _torch()
-    nbuf = 2
+    nbuf = len(stt["din"])
     din, dout, s_h2d, s_d2h = stt["din"], stt["dout"], stt["h2d"], stt["d2h"]
     ws = workspace(device, plan.lib.workspace_bytes(plan.handle, chunk))
     ev_h2d = [torch.cuda.Event() for _ in range(nbuf)]
