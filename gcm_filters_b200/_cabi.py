@@ -173,9 +173,14 @@ def get_library():
         if _lib is None:
             from . import build as _build
 
-            if _build.is_stale():
-                raise GcmfError(f"{LIB_PATH} was built from different sources than the ones in the tree; "
-                                "rebuild with `python -m gcm_filters_b200.build`")
+            if not os.path.isfile(LIB_PATH) or _build.is_stale():
+                # missing, or built from other sources than the ones in the tree: rebuild in place with nvcc
+                # (about 45 s); without a toolchain this raises -- there is no fallback to anything else
+                try:
+                    _build.build(force=True)
+                except Exception as exc:
+                    raise GcmfError(f"{LIB_PATH} is missing or out of date and could not be rebuilt ({exc}); "
+                                    "run `python -m gcm_filters_b200.build`. gcm_filters_b200 has no CPU fallback.")
             lib = Library(LIB_PATH)
             if lib.lib.gcmf_sm_arch() != 100:
                 raise GcmfError(f"{LIB_PATH} is not an sm_100a build")

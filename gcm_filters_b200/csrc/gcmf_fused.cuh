@@ -12,8 +12,8 @@
 //     (nan_to_num, times the wet mask for REGULAR5) of T_{i-1} in a work tile: that is all a neighbour
 //     ever needs, so nan_to_num runs once per produced value instead of once per read;
 //   * k steps ping-pong between two work tiles on a region that shrinks by one cell per step
-//     (overlapped / ghost-zone tiling); own-row neighbours come from registers, the rows above and
-//     below and the W/E columns from the work tile;
+//     (overlapped / ghost-zone tiling); the thread's own rows and the rows above / below and the W/E
+//     columns are read from the work tile;
 //   * the running filtered field `bar` stays in registers for the k steps; T_{i+k-1}, T_{i+k-2} and
 //     bar are written back from registers;
 //   * FLUX: the coefficient tiles (ce, cn, ra) are staged once per CTA and reused for every level; warps
@@ -543,8 +543,8 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
         tl.store(tid, l, st);
     }
     } else {
-    // Neighbour-only synchronisation instead of a CTA barrier per step.  A warp covers half a tile row
-    // group (32 threads x R rows); in phase g (g = it*(k+1) + s, s = 0 for extract) it reads rows published
+    // Neighbour-only synchronisation instead of a CTA barrier per step.  A warp covers 32 threads x R rows of a
+    // tile row group; in phase g (g = it*(k+1) + s, s = 0 for extract) it reads rows published
     // in phase g-1 by the warps above / below it and by the other half of its own rows, and overwrites
     // rows those same warps read in phase g-1.  Both hazards are covered by one rule: start phase g only
     // when these (up to four) neighbour warps have completed phase g-1.  Warps therefore drift apart by up to one phase per
