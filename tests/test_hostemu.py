@@ -145,3 +145,27 @@ def test_c_abi_argument_checks():
     with pytest.raises(_cabi.GcmfError, match="latitude band"):
         lib.filter(band, 1, spec, out, base, ws.size - 256)
     lib.plan_destroy(band)
+
+
+@pytest.mark.parametrize("shape", [(33, 40), (40, 136)])  # the second shape takes the fused path for REGULAR*
+@pytest.mark.parametrize("g", ["REGULAR", "REGULAR_AREA_WEIGHTED", "VECTOR_C_GRID", "VECTOR_B_GRID"])
+def test_nan_semantics_of_unmasked_and_vector_operators(g, shape):
+    """SURVEY note N1: REGULAR has no nan_to_num (NaNs spread through the stencil), the vector operators zero
+    NaNs inside the Laplacian but keep them in the `-x` term of the recurrence."""
+    shape = (33, 40)
+    fields, gv = fixtures.fixture(g, shape)
+    fields = tuple(f.copy() for f in fields)
+    fields[0][7, 9] = np.nan
+    fields[-1][20, 31] = np.nan
+    lap = ALL_KERNELS[GridType[g]](**gv)
+    fa, spec = spec_for(g, gv, filter_scale=4.0, dx_min=1.0)
+    ref = np_oracle.apply_filter(g, gv, fields, **fa)
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    got = EmuPlan(lap, np.float64, *shape).filter(fields, spec.p, _shift_scale(spec, lap))
+    for a, b in zip(got, ref):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.isnan(b).sum() >= 1
+        if g in BIT_EXACT:
+            assert np.array_equal(a, b, equal_nan=True)
+        else:
+            assert rel_l2(a, b) < 1e-12
