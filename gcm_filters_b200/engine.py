@@ -3,6 +3,7 @@
 PyTorch is used for plumbing only -- device memory (tensors own every pointer handed to the
 library), pinned staging, streams.  All arithmetic of the hot path happens inside libgcmf.so.
 """
+import os
 import threading
 
 import numpy as np
@@ -12,7 +13,8 @@ from . import _cabi
 _DT = {np.dtype(np.float32): _cabi.GCMF_F32, np.dtype(np.float64): _cabi.GCMF_F64}
 
 # Temporal blocking of the Chebyshev steps: 0 = auto (fuse up to 4 steps per HBM round trip whenever the
-# operator/grid has a fused kernel), 1 = never fuse, 2..4 = cap.  Results are bit-identical either way.
+# operator/grid has a fused kernel), 1 = never fuse, 2..4 = cap.  Results are bit-identical either way (equal to
+# rounding next to a tripolar fold, where mirrored halo cells sum their fluxes in the opposite order).
 STEPS_PER_BLOCK = 0
 
 
@@ -33,6 +35,15 @@ def _torch():
 
 def _is_torch(a):
     return hasattr(a, "detach") and hasattr(a, "device")
+
+
+def _float_dtype_of(a):
+    """numpy float32 / float64 dtype of an input array; anything else (ints, half, bfloat16) computes in float64."""
+    try:
+        dt = np.dtype(str(a.dtype).replace("torch.", "")) if _is_torch(a) else np.asarray(a).dtype
+    except TypeError:
+        return np.dtype(np.float64)
+    return dt if dt.kind == "f" and dt.itemsize in (4, 8) else np.dtype(np.float64)
 
 
 # ------------------------------------------------------------------------------------------
@@ -58,11 +69,11 @@ class DevicePlan:
                 pl = spec.mask
                 if pl is None:
                     continue
-                t = torch.as_tensor(np.ascontiguousarray(pl), dtype=torch.uint8).to(self.device)
+                t = torch.as_tensor(np.require(pl, requirements=["C", "W"]), dtype=torch.uint8).to(self.device)
             else:
                 if pl is None:
                     continue
-                t = torch.as_tensor(np.ascontiguousarray(pl)).to(device=self.device, dtype=tdt)
+                t = torch.as_tensor(np.require(pl, requirements=["C", "W"])).to(device=self.device, dtype=tdt)
             if tuple(t.shape[-2:]) != (ny, nx):
                 raise ValueError(f"grid variable plane has shape {tuple(t.shape)}, field has (..., {ny}, {nx})")
             bshape = tuple(int(s) for s in t.shape[:-2])
@@ -166,18 +177,15 @@ class _Staged:
         self.ny, self.nx = shape[-2], shape[-1]
         self.batch_shape = shape[:-2]
         self.nb = int(np.prod(self.batch_shape)) if self.batch_shape else 1
+        in_dtype = _float_dtype_of(f0)
         if self.kind == "torch":
-            in_dtype = np.dtype(str(f0.dtype).replace("torch.", ""))
             self.src_device = f0.device
             self.device = f0.device if f0.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
             self.pinned = f0.device.type == "cpu" and f0.is_pinned()
         else:
-            in_dtype = f0.dtype
             self.src_device = None
             self.device = torch.device("cuda", torch.cuda.current_device())
             self.pinned = False
-        if in_dtype.kind != "f" or in_dtype.itemsize not in (4, 8):
-            in_dtype = np.dtype(np.float64)
         self.np_dtype = lap.compute_dtype(in_dtype)
         tdt = torch.float32 if self.np_dtype == np.float32 else torch.float64
         self.tdt = tdt
@@ -243,7 +251,7 @@ def run_laplacian(lap, fields):
 # the filter of chunk i and the D2H copy of chunk i-1 overlap (three streams, event-chained).  Copies are
 # truly asynchronous only from / to pinned memory (torch CPU tensors with pin_memory, or `out=` pinned).
 PIPELINE_MIN_CHUNKS = 4
-PIPELINE_TARGET_CHUNKS = int(__import__("os").environ.get("GCMF_PIPELINE_CHUNKS", "8"))
+PIPELINE_TARGET_CHUNKS = int(os.environ.get("GCMF_PIPELINE_CHUNKS", "8"))
 PIPELINE_MAX_CHUNK_BYTES = 1 << 30
 PIPELINE_NBUF = 2  # device-side input / output chunk buffers in flight
 _pipe_lock = threading.Lock()
@@ -298,7 +306,12 @@ def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
     if out is not None:
         out = tuple(out) if isinstance(out, (tuple, list)) else (out,)
         results = list(out)
-        host_out = [_host_view(o, nb, ny, nx) for o in out]
+        host_out = []
+        for o in out:  # results must land in the caller's memory: no silent copies
+            t = o if _is_torch(o) else torch.from_numpy(o)
+            if tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+                raise ValueError("`out` must be a C-contiguous array with the shape of the input field")
+            host_out.append(t.reshape((nb, ny, nx)))
     else:
         pin = _is_torch(fields[0]) and fields[0].is_pinned()
         host_out = [torch.empty((nb, ny, nx), dtype=tdt, pin_memory=pin) for _ in range(ncomp)]
@@ -377,10 +390,7 @@ def _wants_pipeline(lap, fields, out):
     shape = tuple(f0.shape)
     if len(shape) <= 2 or len(fields) != lap.ncomp or any(tuple(f.shape) != shape for f in fields):
         return None
-    in_dtype = np.dtype(str(f0.dtype).replace("torch.", "")) if _is_torch(f0) else np.asarray(f0).dtype
-    if in_dtype.kind != "f" or in_dtype.itemsize not in (4, 8):
-        in_dtype = np.dtype(np.float64)
-    np_dtype = lap.compute_dtype(in_dtype)
+    np_dtype = lap.compute_dtype(_float_dtype_of(f0))
     planes = [pl for pl in lap._planes.planes if pl is not None] + ([lap._planes.mask] if lap._planes.mask is not None else [])
     if any(np.ndim(pl) > 2 for pl in planes):
         return None
