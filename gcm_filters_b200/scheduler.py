@@ -13,6 +13,14 @@ can only chunk batch dimensions and never splits the two filtered dimensions.
   NCCL point-to-point (``batch_isend_irecv``) over NVLink.  ``T_{i-2}`` and the running ``bar`` are
   point-wise and need no halo.  y is periodic for the non-tripolar grids, so the bands form a ring; for
   tripolar grids the top band folds onto itself locally and row 0 is land, so there is no wrap link.
+* :class:`PeerBandedFilter` -- the same decomposition with the exchange fused into the step kernels: band
+  buffers in symmetric memory, border rows stored straight into the neighbours' ghost rows over NVLink,
+  flag-synchronised (``gcmf_cheb_step_halo``).  One launch per step and rank, no NCCL on the data path.
+* :class:`FusedBandedFilter` -- bands driven by the temporally blocked kernel (scalar operators, periodic
+  grids): four ghost rows, one exchange per 4-step block, by NCCL or by pulling from peer memory.
+
+Measured strong scaling: cfg5 on 8 GPUs 2.0x with NCCL per step vs 5.9x with the fused
+peer-memory exchange; cfg3 (8 levels) with fused bands 5.7x on 8 GPUs.
 """
 import numpy as np
 
