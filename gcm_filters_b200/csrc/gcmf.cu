@@ -670,12 +670,13 @@ template <typename T> static int fused_kind_t(const gcmf_plan* p) {
     using G = FusedGeom<T>;
     const int fl = p->desc.flags;
     if (p->desc.nx % G::AV || p->desc.nx < G::TW || p->desc.ny < G::TH) return -1;
-    const int tripolar = GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S;  // both or neither: a whole (un-banded) tripolar grid
-    if ((fl & tripolar) != 0 && (fl & tripolar) != tripolar) return -1;
+    const int tripolar = GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S;
     // A latitude band (no WRAP_Y) may use the fused path too: the caller keeps FUSED_H ghost rows of the
-    // fields and of every plane on each side of the band and exchanges them after every block.
+    // fields and of every plane on each side of the band and exchanges them after every block.  A whole
+    // tripolar grid carries both FOLD_N and CUT_S; of its bands only the top one folds and only the bottom
+    // one is cut.
     const bool band = !(fl & GCMF_FLAG_WRAP_Y);
-    if (band && (fl & tripolar)) return -1;
+    if (!band && (fl & tripolar) != 0 && (fl & tripolar) != tripolar) return -1;
     const int base = (fl & ~tripolar) | GCMF_FLAG_WRAP_Y;
     if (p->desc.op == GCMF_OP_FLUX) {
         if (base != (GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM)) return -1;

@@ -421,7 +421,8 @@ class FusedBandedFilter(BandedFilter):
     """Latitude bands driven by the temporally blocked kernel: every rank keeps ``H = 4`` ghost rows per side,
     runs up to four Chebyshev steps per launch (``gcmf_cheb_fused`` on a band plan) and exchanges the ghost
     rows of ``T_{i+k-1}`` and ``T_{i+k-2}`` **once per block** instead of once per step (north_star item 3:
-    "per-step-block halo exchange").  Scalar FLUX / REGULAR5 operators on doubly periodic grids; the band must
+    "per-step-block halo exchange").  Scalar FLUX / REGULAR5 operators on doubly periodic or tripolar grids (the
+    top band folds onto itself inside the kernel, the bottom band has no southern neighbour); every band must
     be at least one tile high (32 rows) and ``nx`` a multiple of the vector width.
 
     ``exchange="nccl"``: pack, grouped NCCL send/recv, unpack.  ``exchange="peer"``: the ghosted arrays live in
@@ -444,9 +445,6 @@ class FusedBandedFilter(BandedFilter):
         gc.collect()
 
     def _fused_plan(self, np_dtype, ny, nx):
-        flags_all = self.lap._planes.flags
-        if flags_all & (_cabi.FLAG_FOLD_N | _cabi.FLAG_CUT_S):
-            raise NotImplementedError("fused band decomposition supports doubly periodic grids")
         H = 4
         h, keep, j0, j1, flags = self._plan(np_dtype, ny, nx, halo=H)
         if self.lib.fused_max_steps(h) < H:
@@ -495,17 +493,21 @@ class FusedBandedFilter(BandedFilter):
     def _exchange_ghosts(self, st, idxs):
         """Fill the H ghost rows on both sides of the arrays `idxs` (owned rows sit at [H, H+nyl))."""
         H, nyl = st["H"], st["nyl"]
+        fl = self.lap._planes.flags
+        ring = bool(fl & _cabi.FLAG_WRAP_Y) and not (fl & _cabi.FLAG_CUT_S)  # tripolar grids do not wrap in y
         if st["peers"] is None:
             for k in idxs:  # NCCL send/recv on the rows actually in use
-                self._exchange(st["arrays"][k][..., :nyl + 2 * H, :], True, H)
+                self._exchange(st["arrays"][k][..., :nyl + 2 * H, :], ring, H)
             return
         pr = st["peers"]
         pr["hdl"].barrier(channel=0)  # every rank has finished writing its owned rows (and reading old ghosts)
         ns = pr["nyl_south"]
         for k in idxs:
             mine = st["arrays"][k]
-            mine[..., 0:H, :].copy_(pr["south"][k][..., ns:ns + H, :])                    # its top owned rows
-            mine[..., H + nyl:2 * H + nyl, :].copy_(pr["north"][k][..., H:2 * H, :])      # its bottom owned rows
+            if ring or self.rank != 0:
+                mine[..., 0:H, :].copy_(pr["south"][k][..., ns:ns + H, :])                # its top owned rows
+            if ring or self.rank != self.world - 1:
+                mine[..., H + nyl:2 * H + nyl, :].copy_(pr["north"][k][..., H:2 * H, :])  # its bottom owned rows
 
     def run(self, st):
         import torch

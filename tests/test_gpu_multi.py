@@ -59,12 +59,17 @@ def _worker(rank, world, port, g, shape, q):
         ok = ok and (pj0, pj1) == (j0, j1) and all(np.array_equal(o, s[..., j0:j1, :], equal_nan=True)
                                                    for o, s in zip(pouts, single))
         pbf.close()
-        if g == "IRREGULAR_WITH_LAND":  # temporal blocking on bands: 4 ghost rows, one NCCL exchange per block
+        if g != "VECTOR_C_GRID":  # temporal blocking on bands: 4 ghost rows, one exchange per 4-step block
             for exch in ("nccl", "peer"):
                 fbf = FusedBandedFilter(flt, rank, world, exchange=exch)
                 for _ in range(2):
                     fouts, (fj0, fj1) = fbf.apply(*fields)
-                ok = ok and (fj0, fj1) == (j0, j1) and np.array_equal(fouts[0], single[0][..., j0:j1, :], equal_nan=True)
+                ref_band = single[0][..., j0:j1, :]
+                same_nan = np.array_equal(np.isnan(fouts[0]), np.isnan(ref_band))
+                wet = ~np.isnan(ref_band)
+                err = np.linalg.norm(fouts[0][wet] - ref_band[wet]) / np.linalg.norm(ref_band[wet])
+                # bit-identical on periodic grids; next to a tripolar fold mirrored cells sum in the opposite order
+                ok = ok and (fj0, fj1) == (j0, j1) and same_nan and (err == 0.0 if g == "IRREGULAR_WITH_LAND" else err < 1e-14)
                 fbf.close()
         # batch sharding with an all-gather of the slabs
         full = (apply_batch_sharded(lambda a: flt.apply(a, None), fields[0], rank, world, gather=True)
@@ -83,7 +88,7 @@ def test_banded_and_sharded_match_single_gpu(g):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, g, (90, 160) if g != "IRREGULAR_WITH_LAND" else (96, 264), q))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, g, (90, 160) if g == "VECTOR_C_GRID" else (96, 264), q))
              for r in range(world)]
     for p in procs:
         p.start()

@@ -137,7 +137,9 @@ def _fused_band_worker(rank, world, port, g, shape, dtype, q):
 
 
 @pytest.mark.parametrize("g,dtype,tol", [("IRREGULAR_WITH_LAND", np.float64, 1e-12), ("REGULAR_WITH_LAND", np.float64, 1e-15),
-                                         ("REGULAR_WITH_LAND_AREA_WEIGHTED", np.float32, 1e-5)])
+                                         ("REGULAR_WITH_LAND_AREA_WEIGHTED", np.float32, 1e-5),
+                                         ("TRIPOLAR_POP_WITH_LAND", np.float64, 1e-12),
+                                         ("TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED", np.float64, 1e-12)])
 @pytest.mark.parametrize("world", [2, 3])
 def test_fused_band_decomposition(g, dtype, tol, world):
     """Temporal blocking on latitude bands: 4 ghost rows, one exchange per 4-step block."""
