@@ -24,7 +24,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np

@@ -4,7 +4,6 @@ FilterSpec known answers, operator registry (tests/test_kernels.py:39-61), grid 
 import ctypes
 import os
 import re
-import warnings
 
 import numpy as np
 import pytest

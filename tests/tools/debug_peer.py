@@ -19,7 +19,7 @@ t.fill_(rank + 1); torch.cuda.synchronize(); dist.barrier()
 peer = hdl.get_buffer((rank + 1) % world, (16,), torch.uint8, 0)
 log("peer read", peer[:4].tolist())
 from gcm_filters_b200 import Filter, GridType
-from gcm_filters_b200.scheduler import PeerBandedFilter, BandedFilter
+from gcm_filters_b200.scheduler import PeerBandedFilter
 from oracle import fixtures
 (f,), gv = fixtures.fixture("IRREGULAR_WITH_LAND", (90, 160))
 fb = np.stack([f, f * f])

@@ -1,6 +1,6 @@
-import os, sys, time, json
+import sys, time
 sys.path.insert(0, '.')
-import numpy as np, torch
+import torch
 import bench_inputs
 from gcm_filters_b200 import Filter, FilterShape, GridType, engine
 cfg = bench_inputs.cfg3(nb=62)

@@ -2,7 +2,7 @@
     compute-sanitizer --tool memcheck python tests/tools/sanitize_small.py"""
 import sys, numpy as np
 sys.path.insert(0, '.')
-from gcm_filters_b200 import Filter, GridType, engine
+from gcm_filters_b200 import Filter, GridType
 from oracle import fixtures, np_oracle
 for g, shape in (("IRREGULAR_WITH_LAND", (70, 250)), ("REGULAR_WITH_LAND", (64, 256)), ("TRIPOLAR_POP_WITH_LAND", (66, 140)), ("VECTOR_C_GRID", (40, 70))):
     fields, gv = fixtures.fixture(g, shape)
