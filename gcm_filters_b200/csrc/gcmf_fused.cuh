@@ -36,6 +36,17 @@ enum : int { FK_FLUX = 0, FK_REG5 = 1 };
 
 constexpr int FUSED_H = 4;  // halo width = max fused steps
 
+// Compile-time switches of the fused kernels (kept so that each can be A/B-measured with -D...=0):
+#ifndef GCMF_OPT_SKIPLAST
+#define GCMF_OPT_SKIPLAST 1  // the last step of a block does not publish its result in shared memory
+#endif
+#ifndef GCMF_OPT_POLLWAIT
+#define GCMF_OPT_POLLWAIT 0  // neighbour waits poll mbarrier.test_wait instead of the parking try_wait
+#endif
+#ifndef GCMF_OPT_FASTNAN
+#define GCMF_OPT_FASTNAN 1   // FLUX: warp vote skips nan_to_num when every produced value is finite
+#endif
+
 // XS: how the tile row is split over threads.  1: one 16-byte vector per thread and row (512 threads, used by
 // the register-heavy FLUX kernel); 2: half a vector (1024 threads: the light REGULAR5 steps hide their latency
 // better with twice the warps -- measured +8 % on cfg2, while FLUX loses 30 % with 64 registers per thread).
@@ -90,6 +101,15 @@ template <typename T, int XS> struct FusedThread {  // per-thread registers that
     uint64_t wfbits;                            // REG5: wet_fac (0..4) of own point, 4 bits each
 };
 
+// true if the predicate holds on any (converged) lane of the warp; the host emulator runs one thread at a time
+GCMF_HD bool warp_any(bool p) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(__activemask(), p) != 0;
+#else
+    return p;
+#endif
+}
+
 GCMF_HD int wrap_index(int v, int n) {
     v %= n;
     return v < 0 ? v + n : v;
@@ -116,6 +136,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, unsigned parity) {
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(mb)), "r"(parity) : "memory");
+}
+// non-blocking variant: polls instead of letting the hardware park the warp (A/B switch GCMF_OPT_POLLWAIT)
+__device__ __forceinline__ void mbar_poll(uint64_t* mb, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "POLL_%=:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PDONE_%=;\n"
+        "bra POLL_%=;\n"
+        "PDONE_%=:\n"
         "}\n" ::"r"(smem_u32(mb)), "r"(parity) : "memory");
 }
 // ---- drain counter of the landing tiles (acquire-release at CTA scope) ----
@@ -339,7 +371,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
     // phase: recurrence step s (1-based) on the region [s, TH-s) x [s, TW-s); S = source work tile, D = destination.
     // X1 holds T_{i-1} (raw), X2 holds T_{i-2}; the new T_i is written over X2, so consecutive steps just swap
     // the roles of the two register arrays (no moves).  ALLROWS: the thread's R rows all lie in the region for
-    // every s <= H (threads with 0 < ty < NTY-1), which removes every branch from the row loop.
+    // every s <= H (its rows are core rows), which removes every branch from the row loop.
     template <bool ALLROWS>
     GCMF_HD void step_rows(int tid, int s, const T* __restrict__ S, T* __restrict__ D, T (&X1)[G::R][G::VX],
                            T (&X2)[G::R][G::VX], Thread& st) const {
@@ -353,6 +385,12 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         const T c = (T)P.c;
         const double pk = P.p[s - 1];
         const bool start = is_first() && s == 1;  // recurrence step 1: T_1 = A(x), bar = p0 x + p1 T_1
+        // Nobody reads what the block's last step would publish (the next level starts from the landing tiles).
+        const bool publish = !GCMF_OPT_SKIPLAST || s < P.k;
+        // FLUX, inner threads: publish after the row loop, and skip nan_to_num altogether when no lane of the warp
+        // produced a NaN / inf (sanitize is the identity on finite values, so the vote is only a shortcut).
+        constexpr bool DEFER = GCMF_OPT_FASTNAN && ALLROWS && KIND == FK_FLUX;
+        constexpr bool CONTRACT = GCMF_OPT_CONTRACT && KIND == FK_FLUX;  // as OpFlux in the one-step kernels
         T o[G::R][G::VX], os[G::VX], on[G::VX];
 #pragma unroll
         for (int q = 0; q < G::R; ++q) Ld<T, G::VX>::go(Sc + q * G::TW, o[q]);  // = sanitize(X1), published by this thread
@@ -394,7 +432,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                     const T lap = flux_lap<T>(o[q][v], o_w, o_e, o_n, o_s, ce[v], v == 0 ? cew : ce[v > 0 ? v - 1 : 0],
                                               cn[v], cs[v], ra[v]);
                     const T a = shifted_flux<T>(X1[q][v], c, lap);  // filter.py:171
-                    t0[v] = start ? a : T(2) * a - X2[q][v];        // filter.py:192-194 / 197-203
+                    t0[v] = start ? a : cheb_next<T>(a, X2[q][v]);  // filter.py:192-194 / 197-203
                     cn_prev[v] = cn[v];
                 }
                 have_prev = true;
@@ -415,17 +453,39 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                         lap = (((T(-4) * o[q][v] + o_e) + o_w) + o_n) + o_s;
                     }
                     const T a = -X1[q][v] - c * lap;
-                    t0[v] = start ? a : T(2) * a - X2[q][v];
+                    t0[v] = start ? a : cheb_next<T>(a, X2[q][v]);
                 }
             }
 #pragma unroll
             for (int v = 0; v < G::VX; ++v) {
-                st.acc[q][v] = start ? (T)(P.p0 * (double)X1[q][v] + pk * (double)t0[v])   // filter.py:195
-                                     : (T)((double)st.acc[q][v] + pk * (double)t0[v]);     // filter.py:204
+                const double b0 = start ? P.p0 * (double)X1[q][v] : (double)st.acc[q][v];
+                st.acc[q][v] = (T)bar_update<CONTRACT>(b0, pk, (double)t0[v]);  // filter.py:195 / 204
                 X2[q][v] = t0[v];                                               // T_i replaces T_{i-2}
-                pub[v] = sanitize(t0[v], (st.mbits >> (q * G::VX + v)) & 1u);
             }
-            St<T, G::VX>::go(D + off0 + q * G::TW, pub);
+            if (!DEFER && publish) {
+#pragma unroll
+                for (int v = 0; v < G::VX; ++v) pub[v] = sanitize(t0[v], (st.mbits >> (q * G::VX + v)) & 1u);
+                St<T, G::VX>::go(D + off0 + q * G::TW, pub);
+            }
+        }
+        if (DEFER && publish) {
+            bool nf = false;
+#pragma unroll
+            for (int q = 0; q < G::R; ++q)
+#pragma unroll
+                for (int v = 0; v < G::VX; ++v) nf = nf || nonfinite(X2[q][v]);
+            if (warp_any(nf)) {
+#pragma unroll
+                for (int q = 0; q < G::R; ++q) {
+                    T pub[G::VX];
+#pragma unroll
+                    for (int v = 0; v < G::VX; ++v) pub[v] = sanitize(X2[q][v], true);
+                    St<T, G::VX>::go(D + off0 + q * G::TW, pub);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < G::R; ++q) St<T, G::VX>::go(D + off0 + q * G::TW, X2[q]);
+            }
         }
     }
 
@@ -434,7 +494,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         if (lc0 + G::VX <= s || lc0 >= G::TW - s) return;  // column group outside the region
-        const bool inner = ty > 0 && ty < G::NTY - 1;      // G::R >= H: rows of inner threads are always inside
+        const bool inner = ty * G::R >= G::H && (ty + 1) * G::R <= G::TH - G::H;  // rows inside for every s <= H
         if (s & 1) {
             if (inner) step_rows<true>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
             else step_rows<false>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
@@ -508,7 +568,7 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
     }
     if (tid == 32) *reinterpret_cast<uint32_t*>(mb + 2 + 2 * 32) = 0u;  // drain counter
     if (tid < 32) fence_mbar_init();
-    static_assert(G::TH <= 32 && G::R >= G::H, "one refill lane per tile row; inner threads own only in-region rows");
+    static_assert(G::TH <= 32 && G::NTHREADS <= 1024, "one refill lane per tile row");
     __syncthreads();
     if (tid < G::TH) {
         if (KIND == FK_FLUX) {
@@ -567,7 +627,11 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
     if (lane == 3 && wy < G::NTY - 1) nb_warp = warp + WPR;
     auto wait_neighbours = [&](uint32_t need) {  // all neighbours have completed phase `need`
         if (need == 0) return;
+#if GCMF_OPT_POLLWAIT
+        mbar_poll(&nbar[warp * 2 + (need & 1u)], ((need - 1u) >> 1) & 1u);
+#else
         mbar_wait(&nbar[warp * 2 + (need & 1u)], ((need - 1u) >> 1) & 1u);
+#endif
     };
     auto publish = [&](uint32_t done) {  // this warp has completed phase `done`
         __syncwarp();

@@ -245,6 +245,33 @@ GCMF_HD T flux_lap(T oc, T ow, T oe, T on, T os, T ce, T cew, T cn, T cs, T ra) 
 // shifted Laplacian A(x) = -x - c*Lap (filter.py:171) for the flux family: one fma
 template <typename T> GCMF_HD T shifted_flux(T x, T c, T lap) { return fma_(-c, lap, -x); }
 
+// T_i = 2 A(T_{i-1}) - T_{i-2} (filter.py:197-203) as one fma: 2*a is exact, so the bits are those of (2*a) - t2.
+template <typename T> GCMF_HD T cheb_next(T a, T t2) { return fma_(T(2), a, -t2); }
+// bar + p_i T_i in fp64 (filter.py:204; 195 with bar = p0 x).  CONTRACT: one rounding (the flux family, whose parity
+// is a tolerance); otherwise numpy's two roundings (the families that are bit-exact to the reference).
+#ifndef GCMF_OPT_CONTRACT
+#define GCMF_OPT_CONTRACT 1
+#endif
+template <bool CONTRACT> GCMF_HD double bar_update(double bar, double p, double t0) {
+    return (CONTRACT && GCMF_OPT_CONTRACT) ? ::fma(p, t0, bar) : bar + p * t0;
+}
+
+// exponent all ones: NaN or +-inf (what nan2num changes)
+GCMF_HD bool nonfinite(double x) {
+#ifdef __CUDA_ARCH__
+    return ((unsigned)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u;
+#else
+    return !(x - x == 0.0);
+#endif
+}
+GCMF_HD bool nonfinite(float x) {
+#ifdef __CUDA_ARCH__
+    return (__float_as_uint(x) & 0x7f800000u) == 0x7f800000u;
+#else
+    return !(x - x == 0.0f);
+#endif
+}
+
 // =====================================================================================
 // Operators.  apply(P, q, lap, x): lap[c][v] = Laplacian at the VX points, x[c][v] = raw centre
 // values of P.t1 (NaNs kept: the reference's `-field` term uses the raw field, filter.py:171).
@@ -461,7 +488,7 @@ GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&l
             if (HALO) halo_push_row<T, VX>(P, k, b, j, i0, a);
 #pragma unroll
             for (int v = 0; v < VX; ++v)  // filter.py:195
-                outv[v] = (T)(P.p0 * (double)x[k][v] + P.p1 * (double)a[v]);
+                outv[v] = (T)bar_update<FMA_SHIFT>(P.p0 * (double)x[k][v], P.p1, (double)a[v]);
             St<T, VX>::go(barp, outv);
         } else {
             T t2[VX], t0[VX], bar[VX];
@@ -469,8 +496,8 @@ GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&l
             Ld<T, VX>::go(barp, bar);
 #pragma unroll
             for (int v = 0; v < VX; ++v) {
-                t0[v] = T(2) * a[v] - t2[v];                                    // filter.py:197-203
-                outv[v] = (T)((double)bar[v] + P.p1 * (double)t0[v]);           // filter.py:204
+                t0[v] = cheb_next<T>(a[v], t2[v]);                              // filter.py:197-203
+                outv[v] = (T)bar_update<FMA_SHIFT>((double)bar[v], P.p1, (double)t0[v]);  // filter.py:204
             }
             if (MODE == MODE_MID) {
                 St<T, VX>::go(P.t0[k].p + (int64_t)b * P.t0[k].bstride + (int64_t)j * P.t0[k].pitch + i0, t0);
