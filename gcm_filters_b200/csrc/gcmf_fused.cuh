@@ -36,15 +36,22 @@ enum : int { FK_FLUX = 0, FK_REG5 = 1 };
 
 constexpr int FUSED_H = 4;  // halo width = max fused steps
 
-// Compile-time switches of the fused kernels (kept so that each can be A/B-measured with -D...=0):
+// Compile-time switches of the fused kernels, each A/B-measured with tests/tools/build_variant.py + variant_bench.py
+// (cfg3 shape, 62 x 2400 x 3600 fp64, 44 steps, ms per filter call; profiles/variants_r01.md).  The FLUX kernel sits
+// at the 128-register cap of a 512-thread CTA, so anything that costs registers spills and loses more than it saves:
+// all off 109.8 ms (125 registers, no spills) | SKIPLAST+FASTNAN+CONTRACT 131.4 (128 regs, 72 B spilled) |
+// SKIPLAST+CONTRACT 121.1 | FASTNAN+CONTRACT 133.1 | SKIPLAST+FASTNAN 129.7.
 #ifndef GCMF_OPT_SKIPLAST
-#define GCMF_OPT_SKIPLAST 1  // the last step of a block does not publish its result in shared memory
+#define GCMF_OPT_SKIPLAST 0  // the last step of a block does not publish its result in shared memory
 #endif
 #ifndef GCMF_OPT_POLLWAIT
 #define GCMF_OPT_POLLWAIT 0  // neighbour waits poll mbarrier.test_wait instead of the parking try_wait
 #endif
 #ifndef GCMF_OPT_FASTNAN
-#define GCMF_OPT_FASTNAN 1   // FLUX: warp vote skips nan_to_num when every produced value is finite
+#define GCMF_OPT_FASTNAN 0   // FLUX: warp vote skips nan_to_num when every produced value is finite
+#endif
+#ifndef GCMF_OPT_BARPF
+#define GCMF_OPT_BARPF 0     // L2 prefetch of the next level's bar rows: 1 = one bulk prefetch per core row, 2 = per thread
 #endif
 
 // XS: how the tile row is split over threads.  1: one 16-byte vector per thread and row (512 threads, used by
@@ -326,6 +333,37 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         st.wfbits = wf;
     }
 
+    // `bar` is the one array of a block that is loaded synchronously (straight into the accumulator registers at
+    // the top of a level); these hints pull the next level's rows into L2 while the current level is computed, so
+    // that load is an L2 hit.  Prefetches have no architectural effect: results cannot depend on them.
+    GCMF_HD void prefetch_bar_row(int r, int64_t level) const {  // one bulk prefetch per owned tile row (lane r < TH)
+#ifdef __CUDA_ARCH__
+        if (is_first() || !owns_row(r)) return;
+        int w = P.g.nx - cx0;
+        if (w > G::CW) w = G::CW;  // core columns inside the grid: a multiple of the 16-byte vector
+        const T* row = P.bar.p + level * P.bar.bstride + (int64_t)(cy0 + r - G::H) * P.bar.pitch + cx0;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"((unsigned)(w * sizeof(T))) : "memory");
+#else
+        (void)r; (void)level;
+#endif
+    }
+    GCMF_HD void prefetch_bar_own(int tid, int64_t level) const {  // every thread hints the lines of its own points
+#ifdef __CUDA_ARCH__
+        const int tx = tid % G::NTX, ty = tid / G::NTX;
+        if (is_first() || !owns_cols(tx)) return;
+#pragma unroll
+        for (int q = 0; q < G::R; ++q) {
+            const int lr = ty * G::R + q;
+            if (!owns_row(lr)) continue;
+            const T* ptr = P.bar.p + level * P.bar.bstride + (int64_t)(cy0 + lr - G::H) * P.bar.pitch +
+                           (cx0 + tx * G::VX - G::H);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr) : "memory");
+        }
+#else
+        (void)tid; (void)level;
+#endif
+    }
+
     // phase: bar of the owned points from HBM into registers
     GCMF_HD void load_bar(int tid, int64_t level, Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
@@ -594,7 +632,9 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
             fence_proxy_async();
             tl.issue_state_row(tid, l + 1, &mb[1]);
             mbar_expect_tx(&mb[1], tl.state_tx_bytes(tid));
+            if (GCMF_OPT_BARPF == 1) tl.prefetch_bar_row(tid, l + 1);
         }
+        if (GCMF_OPT_BARPF == 2 && l + 1 < l1) tl.prefetch_bar_own(tid, l + 1);
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {
             tl.step(tid, s, st);
@@ -655,8 +695,10 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
             if (lane < G::TH) {
                 tl.issue_state_row(lane, l + 1, &mb[1]);
                 mbar_expect_tx(&mb[1], tl.state_tx_bytes(lane));
+                if (GCMF_OPT_BARPF == 1) tl.prefetch_bar_row(lane, l + 1);
             }
         }
+        if (GCMF_OPT_BARPF == 2 && l + 1 < l1) tl.prefetch_bar_own(tid, l + 1);
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {
             wait_neighbours(g0 + (uint32_t)s);

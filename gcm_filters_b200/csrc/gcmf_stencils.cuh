@@ -250,7 +250,7 @@ template <typename T> GCMF_HD T cheb_next(T a, T t2) { return fma_(T(2), a, -t2)
 // bar + p_i T_i in fp64 (filter.py:204; 195 with bar = p0 x).  CONTRACT: one rounding (the flux family, whose parity
 // is a tolerance); otherwise numpy's two roundings (the families that are bit-exact to the reference).
 #ifndef GCMF_OPT_CONTRACT
-#define GCMF_OPT_CONTRACT 1
+#define GCMF_OPT_CONTRACT 0
 #endif
 template <bool CONTRACT> GCMF_HD double bar_update(double bar, double p, double t0) {
     return (CONTRACT && GCMF_OPT_CONTRACT) ? ::fma(p, t0, bar) : bar + p * t0;

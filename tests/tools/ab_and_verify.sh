@@ -1,0 +1,29 @@
+#!/bin/sh
+# Development tool for one gpurun call: time the A/B variants under build/variants against the in-tree library,
+# run the GPU test-suite on the in-tree build and, if a variant beats it by > 1.5 %, once more on that variant.
+#   gpurun -- 'sh tests/tools/ab_and_verify.sh c00c offpf2 ...'
+V=build/variants
+ARGS="intree=gcm_filters_b200/libgcmf.so"
+for n in "$@"; do ARGS="$ARGS $n=$V/libgcmf_$n.so"; done
+mkdir -p gpurun_out
+timeout 60 python tests/tools/variant_bench.py --reps 4 $ARGS > gpurun_out/variants_final.log 2>&1
+cat gpurun_out/variants_final.log
+timeout 70 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests_intree.log 2>&1
+echo "rc=$?" >> gpurun_out/gpu_tests_intree.log
+tail -n 3 gpurun_out/gpu_tests_intree.log
+best=$(python - <<'PY'
+import json
+rows = [json.loads(l) for l in open("gpurun_out/variants_final.log") if l.startswith("{")]
+base = [r for r in rows if r["variant"] == "intree"][0]["ms"]
+ok = [r for r in rows if r["maxdiff_vs_first"] < 1e-13 and r["nan_out"] == rows[0]["nan_out"]]
+b = min(ok, key=lambda r: r["ms"])
+print(b["variant"] if b["ms"] < 0.985 * base else "intree")
+PY
+)
+echo "best=$best"
+if [ "$best" != "intree" ] && [ -n "$best" ]; then
+    cp "$V/libgcmf_$best.so" gcm_filters_b200/libgcmf.so
+    timeout 45 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > "gpurun_out/gpu_tests_$best.log" 2>&1
+    echo "rc=$?" >> "gpurun_out/gpu_tests_$best.log"
+    tail -n 3 "gpurun_out/gpu_tests_$best.log"
+fi
