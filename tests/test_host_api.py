@@ -160,3 +160,23 @@ def test_no_cpu_fallback_without_gpu():
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(_cabi.GcmfError, match=r"has not been built"):
         _cabi.Library(str(tmp_path / "libgcmf.so"))
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/gcmf.h is valid C99 and libgcmf.so links into a C program with no C++ / Python / torch in sight:
+    tests/cabi/consumer.c makes version queries and argument-check calls (nothing that needs a GPU)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    if not os.path.isfile(_cabi.LIB_PATH):
+        from gcm_filters_b200 import build
+        build.build()
+    exe = str(tmp_path / "consumer")
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cabi", "consumer.c"), "-o", exe, "-L", libdir, "-l:libgcmf.so",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "arch=100" in res.stdout and "unknown op 99" in res.stdout and res.stdout.strip().endswith("ok")
