@@ -53,6 +53,14 @@ constexpr int FUSED_H = 4;  // halo width = max fused steps
 #ifndef GCMF_OPT_BARPF
 #define GCMF_OPT_BARPF 0     // L2 prefetch of the next level's bar rows: 1 = one bulk prefetch per core row, 2 = per thread
 #endif
+#ifndef GCMF_OPT_EDGEREFILL
+// FLUX: who re-arms the landing tiles for the next level.  0: whichever warp drains them last (any of the 16, so the
+// ~300 instructions of address arithmetic and bulk-copy issue land on the critical path of a random inner warp, and
+// through the neighbour barriers on everybody's); 1: always warp 0, an edge warp that owns halo rows only and does
+// 6 of the inner warps' 16 row-steps per level -- it polls the drain counter between its steps.  NOT YET MEASURED
+// (written after the round-1 GPU budget was spent); parity-test on the GPU before switching it on.
+#define GCMF_OPT_EDGEREFILL 0
+#endif
 
 // XS: how the tile row is split over threads.  1: one 16-byte vector per thread and row (512 threads, used by
 // the register-heavy FLUX kernel); 2: half a vector (1024 threads: the light REGULAR5 steps hide their latency
@@ -162,6 +170,11 @@ __device__ __forceinline__ uint32_t atom_add_acqrel_u32(uint32_t* p, uint32_t v)
     uint32_t old;
     asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
     return old;
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -686,25 +699,51 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
         wait_neighbours(g0);
         tl.extract(tid, st);
         publish(g0 + 1);
-        // the last warp to drain the landing tiles refills them for the next level (32 lanes = TH rows)
+        // The landing tiles are refilled for the next level once every warp has drained them (32 lanes = TH rows).
         uint32_t old = 0;
         if (lane == 0) old = atom_add_acqrel_u32(xcount, 1u);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old == (uint32_t)NWARPS * (uint32_t)(it + 1) - 1u && l + 1 < l1) {
+        const uint32_t drained = (uint32_t)NWARPS * (uint32_t)(it + 1);  // counter value when all warps are through
+        auto refill = [&]() {
             fence_proxy_async();
             if (lane < G::TH) {
                 tl.issue_state_row(lane, l + 1, &mb[1]);
                 mbar_expect_tx(&mb[1], tl.state_tx_bytes(lane));
                 if (GCMF_OPT_BARPF == 1) tl.prefetch_bar_row(lane, l + 1);
             }
-        }
+        };
+#if GCMF_OPT_EDGEREFILL
+        // warp 0 re-arms them: it looks at the counter before each of its steps and, at the latest, waits for it
+        // after its last one (every other warp reaches its own extract without any further help from warp 0)
+        bool refill_due = warp == 0 && l + 1 < l1;
+        auto try_refill = [&](bool block) {
+            if (!refill_due) return;
+            uint32_t seen = 0;
+            do {
+                if (lane == 0) seen = ld_acquire_cta_u32(xcount);
+                seen = __shfl_sync(0xffffffffu, seen, 0);
+            } while (block && seen < drained);
+            if (seen >= drained) {
+                refill();
+                refill_due = false;
+            }
+        };
+#else
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == drained - 1u && l + 1 < l1) refill();  // the last warp through does it
+#endif
         if (GCMF_OPT_BARPF == 2 && l + 1 < l1) tl.prefetch_bar_own(tid, l + 1);
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {
+#if GCMF_OPT_EDGEREFILL
+            try_refill(false);
+#endif
             wait_neighbours(g0 + (uint32_t)s);
             tl.step(tid, s, st);
             publish(g0 + (uint32_t)s + 1u);
         }
+#if GCMF_OPT_EDGEREFILL
+        try_refill(true);
+#endif
         tl.store(tid, l, st);
     }
     }
