@@ -17,7 +17,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import emu_backend  # noqa: E402
-from gcm_filters_b200 import Filter, GridType, engine  # noqa: E402
+from gcm_filters_b200 import Filter, GridType  # noqa: E402
+from gcm_filters_b200.filter import _shift_scale  # noqa: E402
 from gcm_filters_b200.kernels import ALL_KERNELS  # noqa: E402
 from oracle import fixtures  # noqa: E402
 
@@ -36,25 +37,19 @@ def main():
                 fa = dict(filter_scale=8.0 * dxm, dx_min=dxm)
             flt = Filter(grid_type=GridType[g], grid_vars=gvt, **fa)
             lap = ALL_KERNELS[GridType[g]](**gvt)
+            c = _shift_scale(flt.filter_spec, flt.laplacian)
             if len(fields) == 2:
                 gpu = list(lap(*fields)) + list(flt.apply_to_vector(*fields, dims=["y", "x"]))
-                emu = list(emu_backend.run_laplacian(lap, fields)) + list(
-                    emu_backend.run_filter(flt.laplacian, flt.filter_spec.p,
-                                           __import__("gcm_filters_b200.filter", fromlist=["x"])._shift_scale(
-                                               flt.filter_spec, flt.laplacian), fields))
             else:
-                from gcm_filters_b200.filter import _shift_scale
                 gpu = [lap(fields[0]), flt.apply(fields[0], dims=["y", "x"])]
-                emu = [emu_backend.run_laplacian(lap, fields)[0],
-                       emu_backend.run_filter(flt.laplacian, flt.filter_spec.p,
-                                              _shift_scale(flt.filter_spec, flt.laplacian), fields)[0]]
+            emu = list(emu_backend.run_laplacian(lap, fields)) + list(
+                emu_backend.run_filter(flt.laplacian, flt.filter_spec.p, c, fields))
             d = max(float(np.max(np.abs(np.nan_to_num(np.asarray(a, dtype=np.float64)) -
                                         np.nan_to_num(np.asarray(b, dtype=np.float64))))) for a, b in zip(gpu, emu))
             same_nan = all(np.array_equal(np.isnan(a), np.isnan(b)) for a, b in zip(gpu, emu))
             worst = max(worst, d)
             print(f"{g:45s} {np.dtype(dtype).name:8s} max|gpu-emu| = {d:.3e}  nan masks equal: {same_nan}", flush=True)
     print("bit-identical" if worst == 0.0 else f"largest difference {worst:.3e}")
-    del engine
 
 
 if __name__ == "__main__":
