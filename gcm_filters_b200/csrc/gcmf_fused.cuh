@@ -342,9 +342,13 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                 // north neighbour of the top row is its mirror image across the fold (kernels.py:461-467)
                 const bool top = fold() && gy == ny - 1;
                 const bool wrap_y = (P.g.flags & FL_WRAP_Y) != 0;
-                const int gyn = top ? ny - 1 : (wrap_y && gy + 1 == ny ? 0 : gy + 1);
+                // A latitude band (no wrap) has H ghost rows in memory on either side; the outermost one has no
+                // neighbour beyond it, and needs none: tile rows 0 and TH-1 are never computed (ASAN find).
+                const int gyn = top ? ny - 1 : (wrap_y ? (gy + 1 == ny ? 0 : gy + 1)
+                                                       : (gy + 1 > ny + G::H - 1 ? ny + G::H - 1 : gy + 1));
                 const int gxn = top ? nx - 1 - gx : gx;
-                const int gys = wrap_y && gy == 0 ? ny - 1 : gy - 1;  // row 0 of a tripolar grid is land: inert
+                // row 0 of a tripolar grid is land: the wrap below it is inert
+                const int gys = wrap_y ? (gy == 0 ? ny - 1 : gy - 1) : (gy - 1 < -G::H ? -G::H : gy - 1);
                 const uint64_t cnt = (m[(int64_t)gy * pitch + gxe] != 0) + (m[(int64_t)gy * pitch + gxw] != 0) +
                                      (m[(int64_t)gyn * pitch + gxn] != 0) + (m[(int64_t)gys * pitch + gx] != 0);
                 wf |= cnt << (4 * idx);

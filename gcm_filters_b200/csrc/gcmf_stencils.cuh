@@ -526,12 +526,20 @@ template <typename T> struct CgridTile {
     static constexpr int NTHREADS = TX * TY;
     static constexpr int SMEM_ELEMS = 4 * SW * SH;
 
-    // row / column index with the plan's boundary rule (periodic x; periodic y or ghost rows)
+    // row / column index with the plan's boundary rule (periodic x; periodic y or ghost rows).  A tile may stick out
+    // of the grid by up to TY / TX points; the stress entries out there feed discarded outputs only, so they are
+    // clamped onto the last addressable row / column instead of being wrapped a second time (found by the ASAN
+    // build of the host emulator: the single wrap read past the end of the planes for nx < 32 or ny < 9, and past
+    // the ghost row of a latitude band whose height is not a multiple of TY).
     static GCMF_HD int wrap_row(const Geo& g, int j) {
-        if (!(g.flags & FL_WRAP_Y)) return j;
-        return j < 0 ? j + g.ny : (j >= g.ny ? j - g.ny : j);
+        if (!(g.flags & FL_WRAP_Y)) return j > g.ny ? g.ny : j;  // band: rows -1 and ny are ghost rows in memory
+        j = j < 0 ? j + g.ny : (j >= g.ny ? j - g.ny : j);
+        return j >= g.ny ? g.ny - 1 : j;
     }
-    static GCMF_HD int wrap_col(const Geo& g, int i) { return i < 0 ? i + g.nx : (i >= g.nx ? i - g.nx : i); }
+    static GCMF_HD int wrap_col(const Geo& g, int i) {
+        i = i < 0 ? i + g.nx : (i >= g.nx ? i - g.nx : i);
+        return i >= g.nx ? g.nx - 1 : i;
+    }
 
     // stage A: entry e of the stress tiles.  sxx-type entries sit at (j0 + r, i0 + cc), sxy-type at (j0-1+r, i0-1+cc).
     static GCMF_HD void stress(const StepParams<T>& P, int b, int j0, int i0, int e, T* sm) {

@@ -17,6 +17,9 @@ _lib = None
 
 def emu_library():
     global _lib
+    if _lib is None and os.environ.get("GCMF_HOSTEMU_LIB"):  # e.g. an ASAN / UBSAN build (tests/tools/asan_fuzz.sh)
+        _lib = _cabi.Library(os.environ["GCMF_HOSTEMU_LIB"])
+        assert _lib.lib.gcmf_sm_arch() == 0
     if _lib is None:
         src = os.path.join(HERE, "..", "gcm_filters_b200", "csrc")
         deps = [os.path.join(src, f) for f in ("gcmf.cu", "gcmf_stencils.cuh", "gcmf_internal.h")]
