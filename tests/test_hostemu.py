@@ -169,3 +169,34 @@ def test_nan_semantics_of_unmasked_and_vector_operators(g, shape):
             assert np.array_equal(a, b, equal_nan=True)
         else:
             assert rel_l2(a, b) < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(41, 48), (24, 37), (9, 20)])
+@pytest.mark.parametrize("g", ["IRREGULAR_WITH_LAND", "VECTOR_C_GRID", "VECTOR_B_GRID",
+                               "REGULAR_WITH_LAND_AREA_WEIGHTED", "TRIPOLAR_POP_WITH_LAND"])
+def test_peer_banded_filter_single_rank(g, shape):
+    """gcmf_halo_push / gcmf_cheb_step_halo (ghost rows stored by the step kernels, flag-synchronised) with one
+    rank that is its own north and south neighbour, buffers in ordinary memory: the bookkeeping of
+    PeerBandedFilter (slab layout, ghost-row addresses, growing flag values across two runs) against the oracle.
+    The multi-GPU version of this test is tests/test_gpu_multi.py."""
+    from gcm_filters_b200 import Filter, FilterShape
+    from gcm_filters_b200.scheduler import PeerBandedFilter
+    from hostemu_util import emu_library
+    if g.startswith("TRIPOLAR") and shape[1] % 2:
+        pytest.skip("the fold pairs column i with nx-1-i")
+    fields, gv = fixtures.fixture(g, shape)
+    fields = tuple(np.stack([f, f * f]) for f in fields)
+    fa = dict(filter_scale=6.0, dx_min=1.0)
+    if g in fixtures.VECTOR_GRIDS:
+        kx, ky = ("dxT", "dyT") if g == "VECTOR_C_GRID" else ("DXU", "DYU")
+        dxm = float(min(gv[kx].min(), gv[ky].min()))
+        fa = dict(filter_scale=6.0 * dxm, dx_min=dxm)
+    flt = Filter(grid_type=GridType[g], grid_vars=gv, filter_shape=FilterShape.GAUSSIAN, **fa)
+    pf = PeerBandedFilter(flt, 0, 1, library=emu_library(), device="cpu")
+    for _ in range(2):  # the second run re-uses the buffers with a new flag epoch
+        outs, (j0, j1) = pf.apply(*fields)
+    assert (j0, j1) == (0, shape[0])
+    ref = np_oracle.apply_filter(g, gv, fields, **fa)
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    for o, r in zip(outs, ref):
+        assert rel_l2(o, r) < 1e-12
