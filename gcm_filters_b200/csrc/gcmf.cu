@@ -462,6 +462,9 @@ template <typename T>
 static int run_step_t(const gcmf_plan* pl, int64_t nb, int mode, const gcmf_field* t1, const gcmf_field* t2,
                       const gcmf_field* t0, const gcmf_field* bar, double p0, double p1, cudaStream_t st,
                       const gcmf_halo* halo = nullptr) {
+    // The C-grid kernels address u and v (read next to each other at every point) with one row pitch.
+    if (pl->desc.op == GCMF_OP_VECTOR_C && t1 && t1[0].pitch != t1[1].pitch)
+        return gcmf_set_error(GCMF_EINVAL, "GCMF_OP_VECTOR_C: the u and v input fields must share one row pitch");
     StepParams<T> P;
     memset(&P, 0, sizeof P);
     P.halo = make_halo<T>(halo);
@@ -688,6 +691,10 @@ template <typename T> static int fused_kind_t(const gcmf_plan* p) {
     }
     if (p->desc.op == GCMF_OP_REGULAR5) {
         const int core = base & ~GCMF_FLAG_AREA;  // prepare / finalize happen outside the recurrence arithmetic
+        // the last block divides by the area with vector loads: a strided / batched area plane takes the one-step path
+        if ((fl & GCMF_FLAG_AREA) &&
+            (!p->plane[1].p || p->plane[1].nb != 1 || !aligned(p->plane[1].p, p->plane[1].pitch, 0, G::AV, sizeof(T))))
+            return -1;
         if (core == GCMF_FLAG_WRAP_Y && !(fl & tripolar)) return FK_REG5;
         if (core == (GCMF_FLAG_WRAP_Y | GCMF_FLAG_MASK | GCMF_FLAG_NAN2NUM) && p->plane[0].p && p->plane[0].nb == 1)
             return FK_REG5;
@@ -892,7 +899,14 @@ extern "C" int gcmf_filter(gcmf_plan* p, int64_t nb, const gcmf_field* in, const
     if (is_band_plan(p))
         return gcmf_set_error(GCMF_EINVAL, "gcmf_filter runs whole (periodic / tripolar) grids; drive a latitude band with "
                                            "gcmf_cheb_step / gcmf_cheb_fused and exchange its ghost rows between calls");
-    if (plan_uses_fused(p)) {
+    // The fused kernels move whole 16-byte vectors (bulk copies, vector stores): caller-provided fields that are not
+    // 16-byte aligned with vector-multiple strides take the one-step kernels (which have a scalar form) instead.
+    const size_t es = p->desc.dtype == GCMF_F64 ? 8 : 4;
+    bool fused_ok = plan_uses_fused(p);
+    for (int k = 0; fused_ok && k < nc; ++k)
+        fused_ok = aligned(out[k].ptr, out[k].pitch, out[k].bstride, (int)(16 / es), es) &&
+                   (area || aligned(in[k].ptr, in[k].pitch, in[k].bstride, (int)(16 / es), es));
+    if (fused_ok) {
         // Temporally blocked path: the whole recurrence (filter.py:191-206) as ceil(n/kmax) launches; the first
         // block performs step 1, the last one finalizes bar.  State ping-pongs between two workspace pairs.
         const int kmax = p->steps_per_block ? p->steps_per_block : FusedGeom<double>::H;

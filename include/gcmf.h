@@ -91,7 +91,11 @@ typedef struct gcmf_plan_desc {
     int32_t device;  /* CUDA device ordinal the plan (and all pointers given to it) lives on  */
 } gcmf_plan_desc;
 
-/* One (nb, ny, nx) field: element (b, j, i) is at ptr[b*bstride + j*pitch + i]. */
+/* One (nb, ny, nx) field: element (b, j, i) is at ptr[b*bstride + j*pitch + i].  Any pitch >= nx and
+ * bstride >= ny*pitch is accepted: 16-byte aligned pointers with pitch and bstride multiples of 16 bytes take the
+ * vector / temporally blocked kernels, anything else their scalar forms (same results).  GCMF_OP_VECTOR_C reads u and
+ * v next to each other at every point and wants ONE row pitch for the two input components (EINVAL otherwise), as
+ * it wants one pitch for its 14 planes. */
 typedef struct gcmf_field {
     void *ptr;
     int64_t pitch;

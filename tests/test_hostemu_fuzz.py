@@ -16,3 +16,34 @@ def test_emulator_matches_oracle_on_random_cases(seed):
     rng = np.random.default_rng(1000 + seed)
     failures = [m for m in (fuzz_hostemu.one_case(rng, k) for k in range(60)) if m]
     assert not failures, failures
+
+
+def test_strided_fields_and_planes_match_contiguous():
+    """C ABI: row pitch > nx, padded batch strides, unaligned base pointers (scalar forms of the vector kernels,
+    one-step path instead of the fused one) give the results of the contiguous call and never write the padding."""
+    import fuzz_pitch
+    rng = np.random.default_rng(77)
+    failures = []
+    for k in range(80):
+        try:
+            msg = fuzz_pitch.one_case(rng, k)
+        except Exception as exc:  # noqa: BLE001
+            msg = f"#{k} raised {type(exc).__name__}: {exc}"
+        if msg:
+            failures.append(msg)
+    assert not failures, failures
+
+
+def test_c_grid_components_must_share_a_pitch():
+    from gcm_filters_b200 import GridType, _cabi
+    from gcm_filters_b200.kernels import ALL_KERNELS
+    from hostemu_util import EmuPlan
+    from oracle import fixtures
+    (u, v), gv = fixtures.fixture("VECTOR_C_GRID", (12, 20))
+    plan = EmuPlan(ALL_KERNELS[GridType.VECTOR_C_GRID](**gv), np.float64, 12, 20)
+    wide = np.zeros((12, 24))
+    wide[:, :20] = v
+    out = [np.zeros((12, 20)), np.zeros((12, 20))]
+    fin = [(u.ctypes.data, 20, 240), (wide.ctypes.data, 24, 288)]
+    with pytest.raises(_cabi.GcmfError, match="share one row pitch"):
+        plan.lib.laplacian(plan.h, 1, fin, [(o.ctypes.data, 20, 240) for o in out])

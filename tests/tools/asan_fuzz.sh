@@ -14,6 +14,7 @@ export LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=lib
 export ASAN_OPTIONS=detect_leaks=0 GCMF_HOSTEMU_LIB="$OUT"
 cd "$ROOT"
 python tests/tools/fuzz_hostemu.py --cases "$N" --seed 3
+python tests/tools/fuzz_pitch.py --cases "$N" --seed 8
 python tests/tools/fuzz_bands.py --cases $((N / 10 + 10)) --seed 9
 python -m pytest tests/test_hostemu.py tests/test_hostemu_fused.py tests/test_reference_suite.py \
     tests/test_scheduler_gloo.py -x -q -m "not gpu"
