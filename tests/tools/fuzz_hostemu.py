@@ -54,8 +54,27 @@ def one_case(rng, k):
         gv["kappa_w"][ny // 2, nx // 2] = 1.0
     fb = [np.stack([f * (1 + 0.1 * b) + 0.05 * rng.standard_normal((ny, nx)) for b in range(nb)]) for f in fields]
     if "wet_mask" in gv and rng.random() < 0.7:
+        junk = [np.nan, np.inf, -np.inf][int(rng.integers(3))]  # nan_to_num: NaN -> 0, +-inf -> +-largest finite
+        if "dxw" in gv or "dxe" in gv or "dxt" in gv:
+            # flux-form operators difference nan_to_num(f) across land-sea faces before masking the face: with +-inf
+            # on land the reference overflows ((1.8e308 - x) / 0.9 = inf, inf * 0 = NaN) and poisons the neighbouring
+            # ocean cells; the precombined face coefficient here is an exact 0.  Undefined input: NaN only.
+            junk = np.nan
         for f in fb:
-            f[:, gv["wet_mask"] == 0] = np.nan
+            f[:, gv["wet_mask"] == 0] = junk
+    elif rng.random() < 0.3:  # a few NaNs in the open ocean: they spread (or are zeroed) exactly as in the reference
+        for f in fb:
+            f[rng.integers(nb), rng.integers(ny), rng.integers(nx)] = np.nan
+    if nb > 1 and not g.startswith("MOM5") and rng.random() < 0.25:
+        # batched grid variables: one plane per batch slice, e.g. a wet mask per depth level
+        for k_ in list(gv):
+            if "mask" in k_:
+                lvl = np.stack([gv[k_] * (rng.random((ny, nx)) > 0.1 * b) for b in range(nb)])
+                if g.startswith("TRIPOLAR"):
+                    lvl[:, 0, :] = 0
+                gv[k_] = lvl
+            elif "kappa" not in k_:
+                gv[k_] = np.stack([gv[k_] * (1.0 + 0.05 * b) for b in range(nb)])
     dxm = 1.0
     if g in fixtures.VECTOR_GRIDS:
         kx, ky = ("dxT", "dyT") if g == "VECTOR_C_GRID" else ("DXU", "DYU")
