@@ -1,6 +1,8 @@
 """Pin the CPU oracle (oracle/np_oracle.py) to the reference: its 18 golden arrays, its FilterSpec
 known-answer tests, outputs of the live reference captured in tests/golden, and -- when the
 reference tree is present (build container only) -- the live reference itself, bit for bit."""
+import os
+
 import numpy as np
 import pytest
 
@@ -101,6 +103,17 @@ def test_live_reference_bit_exact(g):
     fa = vec_args(g, gv, dict(filter_scale=5.0, dx_min=1.0, filter_shape="TAPER", n_steps=12))
     res_ref, flt = ref_loader.ref_filter(g, gv, fields, **fa)
     assert np.array_equal(_stack(np_oracle.apply_filter(g, gv, fields, **fa)), _stack(res_ref))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_live_reference_bit_exact_on_random_cases():
+    """tests/tools/fuzz_oracle_vs_reference.py at suite size: random grid type, shape, batch, land, NaN / inf on land,
+    batched grid variables, fp32 / fp64, both filter shapes; values and dtypes must agree exactly."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "fuzz_oracle_vs_reference.py")
+    res = subprocess.run([sys.executable, tool, "21", "80"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
 
 
 def test_oracle_validation_errors():
