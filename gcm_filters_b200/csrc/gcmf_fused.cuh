@@ -61,6 +61,12 @@ constexpr int FUSED_H = 4;  // halo width = max fused steps
 // (written after the round-1 GPU budget was spent); parity-test on the GPU before switching it on.
 #define GCMF_OPT_EDGEREFILL 0
 #endif
+#ifndef GCMF_OPT_ROWNAN
+// FLUX: publish a row's new values as they are unless one of them is NaN / inf (one test on the exponent bits per
+// value and a branch per row) instead of running the 9-instruction branch-free nan_to_num on every value -- the
+// sanitizer is a third of the step loop's instructions.  Same results by construction.  NOT YET MEASURED.
+#define GCMF_OPT_ROWNAN 0
+#endif
 #ifndef GCMF_OPT_LATEWAIT
 // FLUX: drop the neighbour wait in front of `extract` when the block has an even number of steps.  extract only
 // writes the thread's own points of work tile S0; the neighbours' last step k reads S[(k-1)&1] = S1 for even k, so
@@ -525,7 +531,18 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                 st.acc[q][v] = (T)bar_update<CONTRACT>(b0, pk, (double)t0[v]);  // filter.py:195 / 204
                 X2[q][v] = t0[v];                                               // T_i replaces T_{i-2}
             }
-            if (!DEFER && publish) {
+            if (GCMF_OPT_ROWNAN && KIND == FK_FLUX && !DEFER && publish) {
+                bool nf = false;
+#pragma unroll
+                for (int v = 0; v < G::VX; ++v) nf = nf || nonfinite(t0[v]);
+                if (nf) {
+#pragma unroll
+                    for (int v = 0; v < G::VX; ++v) pub[v] = nan2num(t0[v]);
+                    St<T, G::VX>::go(D + off0 + q * G::TW, pub);
+                } else {
+                    St<T, G::VX>::go(D + off0 + q * G::TW, t0);
+                }
+            } else if (!DEFER && publish) {
 #pragma unroll
                 for (int v = 0; v < G::VX; ++v) pub[v] = sanitize(t0[v], (st.mbits >> (q * G::VX + v)) & 1u);
                 St<T, G::VX>::go(D + off0 + q * G::TW, pub);
