@@ -61,6 +61,16 @@ constexpr int FUSED_H = 4;  // halo width = max fused steps
 // (written after the round-1 GPU budget was spent); parity-test on the GPU before switching it on.
 #define GCMF_OPT_EDGEREFILL 0
 #endif
+#ifndef GCMF_OPT_SANSTATE
+// FLUX: keep the SANITIZED T_{i-1} / T_{i-2} in the per-thread registers, plus one NaN bit and one inf bit per
+// value, instead of the raw values.  The sanitized value is what the Laplacian differences and what is published,
+// so (a) the thread's own rows no longer have to be read back from the work tile (4 of the 19 LDS.128 of a step,
+// and the 16 registers that held them: the kernel sits at the register cap, see above), and (b) nan_to_num runs
+// only for rows that produced a NaN / inf (one exponent test per value otherwise).  The raw value that the
+// point-wise terms "-x" and "- T_{i-2}" need is rebuilt from the bits (NaN, or inf with the sign of the sanitized
+// value), so results are bit-identical (NaN payloads aside).  NOT YET MEASURED; verified in the host emulator only.
+#define GCMF_OPT_SANSTATE 0
+#endif
 #ifndef GCMF_OPT_ROWNAN
 // FLUX: publish a row's new values as they are unless one of them is NaN / inf (one test on the exponent bits per
 // value and a branch per row) instead of running the 9-instruction branch-free nan_to_num on every value -- the
@@ -128,7 +138,15 @@ template <typename T, int XS> struct FusedThread {  // per-thread registers that
     T acc[FusedGeom<T, XS>::R][FusedGeom<T, XS>::VX];  // running bar (owned points)
     uint32_t mbits;                             // REG5: wet bit of own point (q*VX+v)
     uint64_t wfbits;                            // REG5: wet_fac (0..4) of own point, 4 bits each
+    uint32_t nanbits, infbits;                  // SANSTATE: bit (16*a + q*VX+v): raw value of array a (0: t1, 1: t2) was NaN / inf
 };
+
+// SANSTATE: the raw value that nan_to_num turned into s
+template <typename T> GCMF_HD T raw_of(T s, bool was_nan, bool was_inf) {
+    if (was_nan) return (T)NAN;
+    if (was_inf) return s > T(0) ? (T)INFINITY : -(T)INFINITY;
+    return s;
+}
 
 // true if the predicate holds on any (converged) lane of the warp; the host emulator runs one thread at a time
 GCMF_HD bool warp_any(bool p) {
@@ -414,7 +432,56 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
     }
 
     // phase: lift the raw own points out of the landing tiles, publish the sanitized T1 in S0
+    static constexpr bool SANSTATE = GCMF_OPT_SANSTATE && KIND == FK_FLUX;
+    static constexpr uint32_t ROWMASK = (1u << G::VX) - 1u;
+    static_assert(G::R * G::VX <= 16, "SANSTATE keeps 16 flag bits per array");
+
+    // SANSTATE form of extract: registers and S0 receive nan_to_num(T1) (and nan_to_num(T2)), the flag bits remember
+    // what was NaN / inf
+    GCMF_HD void extract_ss(int tid, Thread& st) const {
+        const int tx = tid % G::NTX, ty = tid / G::NTX;
+        const int lc0 = tx * G::VX;
+        const T* X = tileX();
+        const T* Y = tileY();
+        T* S0 = tileS(0);
+        uint32_t nb = 0, ib = 0;
+#pragma unroll
+        for (int q = 0; q < G::R; ++q) {
+            const int off = (ty * G::R + q) * G::TW + lc0;
+            Ld<T, G::VX>::go(X + off, st.t1[q]);
+            if (!is_first()) {
+                Ld<T, G::VX>::go(Y + off, st.t2[q]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < G::VX; ++v) st.t2[q][v] = T(0);
+            }
+            bool nf = false;
+#pragma unroll
+            for (int v = 0; v < G::VX; ++v) nf = nf || nonfinite(st.t1[q][v]) || nonfinite(st.t2[q][v]);
+            if (nf) {
+#pragma unroll
+                for (int v = 0; v < G::VX; ++v) {
+                    const int idx = q * G::VX + v;
+                    const T r1 = st.t1[q][v], r2 = st.t2[q][v];
+                    if (r1 != r1) nb |= 1u << idx;
+                    else if (nonfinite(r1)) ib |= 1u << idx;
+                    if (r2 != r2) nb |= 1u << (16 + idx);
+                    else if (nonfinite(r2)) ib |= 1u << (16 + idx);
+                    st.t1[q][v] = nan2num(r1);
+                    st.t2[q][v] = nan2num(r2);
+                }
+            }
+            St<T, G::VX>::go(S0 + off, st.t1[q]);
+        }
+        st.nanbits = nb;
+        st.infbits = ib;
+    }
+
     GCMF_HD void extract(int tid, Thread& st) const {
+        if (SANSTATE) {
+            extract_ss(tid, st);
+            return;
+        }
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         const T* X = tileX();
@@ -569,12 +636,141 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         }
     }
 
+    // SANSTATE form of step_rows (FLUX only): X1 / X2 hold sanitized values, a1 = 0 when X1 is st.t1 (else 1) selects
+    // their flag bits.  The thread's own rows come from X1, only the rows above / below and the W / E columns from S.
+    // GENERAL = false: no value of the warp's threads is flagged, the row loop is branch-free and free of sanitizer
+    // arithmetic; GENERAL = true: the raw values of the point-wise terms are rebuilt from the flag bits (selects).
+    // Either way the new values are examined after the loop and only a NaN / inf among them (or GENERAL) triggers
+    // nan_to_num and the flag update; the rows are published last.
+    template <bool ALLROWS, bool GENERAL>
+    GCMF_HD void step_rows_ss(int tid, int s, const T* __restrict__ S, T* __restrict__ D, T (&X1)[G::R][G::VX],
+                              T (&X2)[G::R][G::VX], int a1, Thread& st) const {
+        const int tx = tid % G::NTX, ty = tid / G::NTX;
+        const int lc0 = tx * G::VX;
+        const int lr0 = ty * G::R;
+        const int off0 = lr0 * G::TW + lc0;
+        const T* Sc = S + off0;
+        const T* Sw = Sc - (lc0 > 0 ? 1 : 0);
+        const T* Se = Sc + (lc0 + G::VX < G::TW ? G::VX : G::VX - 1);
+        const T c = (T)P.c;
+        const double pk = P.p[s - 1];
+        const bool start = is_first() && s == 1;
+        const bool publish = !GCMF_OPT_SKIPLAST || s < P.k;
+        constexpr bool CONTRACT = GCMF_OPT_CONTRACT != 0;
+        const int f1 = a1 * 16, f2 = (a1 ^ 1) * 16;
+        T os[G::VX], on[G::VX];
+        if (ALLROWS || lr0 > 0) Ld<T, G::VX>::go(Sc - G::TW, os);
+        if (ALLROWS || lr0 + G::R < G::TH) Ld<T, G::VX>::go(Sc + G::R * G::TW, on);
+        T cn_prev[G::VX];
+        bool have_prev = false;
+#pragma unroll
+        for (int q = 0; q < G::R; ++q) {
+            const int lr = lr0 + q;
+            if (!ALLROWS && (lr < s || lr >= G::TH - s)) {
+                have_prev = false;
+                continue;
+            }
+            const T ow = Sw[q * G::TW];
+            const T oe = Se[q * G::TW];
+            const T* CE = tileC(0) + off0 + q * G::TW;
+            const T* CN = tileC(1) + off0 + q * G::TW;
+            const T* RA = tileC(2) + off0 + q * G::TW;
+            T ce[G::VX], cn[G::VX], cs[G::VX], ra[G::VX];
+            Ld<T, G::VX>::go(CE, ce);
+            const T cew = *(CE - (lc0 > 0 ? 1 : 0));
+            Ld<T, G::VX>::go(CN, cn);
+            if ((ALLROWS && q > 0) || have_prev) {
+#pragma unroll
+                for (int v = 0; v < G::VX; ++v) cs[v] = cn_prev[v];
+            } else {
+                Ld<T, G::VX>::go(CN - G::TW, cs);
+            }
+            Ld<T, G::VX>::go(RA, ra);
+#pragma unroll
+            for (int v = 0; v < G::VX; ++v) {
+                const T o_e = v == G::VX - 1 ? oe : X1[q][v + 1 < G::VX ? v + 1 : v];
+                const T o_w = v == 0 ? ow : X1[q][v > 0 ? v - 1 : 0];
+                const T o_n = q == G::R - 1 ? on[v] : X1[q + 1 < G::R ? q + 1 : q][v];
+                const T o_s = q == 0 ? os[v] : X1[q > 0 ? q - 1 : 0][v];
+                const T lap = flux_lap<T>(X1[q][v], o_w, o_e, o_n, o_s, ce[v], v == 0 ? cew : ce[v > 0 ? v - 1 : 0],
+                                          cn[v], cs[v], ra[v]);
+                T x = X1[q][v], t2 = X2[q][v];
+                if (GENERAL) {  // rebuild the raw values of the point-wise terms
+                    const int idx = q * G::VX + v;
+                    x = raw_of<T>(x, (st.nanbits >> (f1 + idx)) & 1u, (st.infbits >> (f1 + idx)) & 1u);
+                    t2 = raw_of<T>(t2, (st.nanbits >> (f2 + idx)) & 1u, (st.infbits >> (f2 + idx)) & 1u);
+                }
+                const T a = shifted_flux<T>(x, c, lap);                  // filter.py:171
+                const T t0 = start ? a : cheb_next<T>(a, t2);            // filter.py:192-194 / 197-203
+                const double b0 = start ? P.p0 * (double)x : (double)st.acc[q][v];
+                st.acc[q][v] = (T)bar_update<CONTRACT>(b0, pk, (double)t0);  // filter.py:195 / 204
+                X2[q][v] = t0;                                           // raw T_i replaces T_{i-2}
+                cn_prev[v] = cn[v];
+            }
+            have_prev = true;
+        }
+        // sanitize what has to be sanitized: nothing, unless a new value is NaN / inf (or flags have to be cleared)
+        bool nf = GENERAL;
+        if (!GENERAL) {
+#pragma unroll
+            for (int q = 0; q < G::R; ++q)
+#pragma unroll
+                for (int v = 0; v < G::VX; ++v)
+                    if (ALLROWS || (lr0 + q >= s && lr0 + q < G::TH - s)) nf = nf || nonfinite(X2[q][v]);
+        }
+        if (nf) {
+#pragma unroll
+            for (int q = 0; q < G::R; ++q) {
+                if (!ALLROWS && (lr0 + q < s || lr0 + q >= G::TH - s)) continue;
+#pragma unroll
+                for (int v = 0; v < G::VX; ++v) {
+                    const uint32_t bit = 1u << (f2 + q * G::VX + v);
+                    const T t0 = X2[q][v];
+                    const bool isn = t0 != t0;
+                    const bool isi = !isn && nonfinite(t0);
+                    st.nanbits = isn ? (st.nanbits | bit) : (st.nanbits & ~bit);
+                    st.infbits = isi ? (st.infbits | bit) : (st.infbits & ~bit);
+                    X2[q][v] = nan2num(t0);
+                }
+            }
+        }
+        if (publish) {
+#pragma unroll
+            for (int q = 0; q < G::R; ++q)
+                if (ALLROWS || (lr0 + q >= s && lr0 + q < G::TH - s)) St<T, G::VX>::go(D + off0 + q * G::TW, X2[q]);
+        }
+    }
+
     // odd steps read T_{i-1} from st.t1 and overwrite st.t2; even steps the other way round
     GCMF_HD void step(int tid, int s, Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         if (lc0 + G::VX <= s || lc0 >= G::TW - s) return;  // column group outside the region
         const bool inner = ty * G::R >= G::H && (ty + 1) * G::R <= G::TH - G::H;  // rows inside for every s <= H
+        if (SANSTATE) {
+            // one code path per warp: the general form as soon as any of its threads holds a flagged value
+            const bool general = warp_any((st.nanbits | st.infbits) != 0u);
+            const T* Ssrc = (s & 1) ? tileS(0) : tileS(1);
+            T* Sdst = (s & 1) ? tileS(1) : tileS(0);
+            if (s & 1) {
+                if (inner) {
+                    if (general) step_rows_ss<true, true>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
+                    else step_rows_ss<true, false>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
+                } else {
+                    if (general) step_rows_ss<false, true>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
+                    else step_rows_ss<false, false>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
+                }
+            } else {
+                if (inner) {
+                    if (general) step_rows_ss<true, true>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
+                    else step_rows_ss<true, false>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
+                } else {
+                    if (general) step_rows_ss<false, true>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
+                    else step_rows_ss<false, false>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
+                }
+            }
+            return;
+        }
         if (s & 1) {
             if (inner) step_rows<true>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
             else step_rows<false>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
@@ -607,10 +803,25 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                 }
             } else {
                 // after an odd number of steps the newest T sits in st.t2 (see step())
+                if (SANSTATE) {  // the arrays in HBM hold raw values
+                    T n1[G::VX], n2[G::VX];
+                    const int fa = (P.k & 1) ? 16 : 0, fb = (P.k & 1) ? 0 : 16;
+#pragma unroll
+                    for (int v = 0; v < G::VX; ++v) {
+                        const int idx = q * G::VX + v;
+                        n1[v] = raw_of<T>((P.k & 1) ? st.t2[q][v] : st.t1[q][v], (st.nanbits >> (fa + idx)) & 1u,
+                                          (st.infbits >> (fa + idx)) & 1u);
+                        n2[v] = raw_of<T>((P.k & 1) ? st.t1[q][v] : st.t2[q][v], (st.nanbits >> (fb + idx)) & 1u,
+                                          (st.infbits >> (fb + idx)) & 1u);
+                    }
+                    St<T, G::VX>::go(P.t1_out.p + level * P.t1_out.bstride + (int64_t)gy * P.t1_out.pitch + gx, n1);
+                    St<T, G::VX>::go(P.t2_out.p + level * P.t2_out.bstride + (int64_t)gy * P.t2_out.pitch + gx, n2);
+                } else {
                 St<T, G::VX>::go(P.t1_out.p + level * P.t1_out.bstride + (int64_t)gy * P.t1_out.pitch + gx,
                                  (P.k & 1) ? st.t2[q] : st.t1[q]);
                 St<T, G::VX>::go(P.t2_out.p + level * P.t2_out.bstride + (int64_t)gy * P.t2_out.pitch + gx,
                                  (P.k & 1) ? st.t1[q] : st.t2[q]);
+                }
             }
             St<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)gy * P.bar.pitch + gx, outv);
         }
