@@ -157,9 +157,20 @@ GCMF_HD bool warp_any(bool p) {
 #endif
 }
 
+#ifndef GCMF_OPT_WRAPONCE
+// Periodic index arithmetic of the tile loaders without the integer division: a fused plan's grid is at least one
+// tile wide and high, so every index handed to wrap_index lies in (-n, 2n) and one conditional add / subtract is
+// the modulo.  The `%` costs ~35 instructions each on the path of the warp that re-arms the landing tiles (four to
+// six of them per lane and level) and per gathered element next to a tripolar fold.  NOT YET MEASURED.
+#define GCMF_OPT_WRAPONCE 0
+#endif
 GCMF_HD int wrap_index(int v, int n) {
+#if GCMF_OPT_WRAPONCE
+    return v < 0 ? v + n : (v >= n ? v - n : v);
+#else
     v %= n;
     return v < 0 ? v + n : v;
+#endif
 }
 
 // ---- bulk async copy global -> shared, completing on an mbarrier (device) / memcpy (host emulator) ----
