@@ -649,11 +649,14 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
 
     // SANSTATE form of step_rows (FLUX only): X1 / X2 hold sanitized values, a1 = 0 when X1 is st.t1 (else 1) selects
     // their flag bits.  The thread's own rows come from X1, only the rows above / below and the W / E columns from S.
-    // GENERAL = false: no value of the warp's threads is flagged, the row loop is branch-free and free of sanitizer
-    // arithmetic; GENERAL = true: the raw values of the point-wise terms are rebuilt from the flag bits (selects).
-    // Either way the new values are examined after the loop and only a NaN / inf among them (or GENERAL) triggers
-    // nan_to_num and the flag update; the rows are published last.
-    template <bool ALLROWS, bool GENERAL>
+    // Three forms, one per warp and step:
+    //   MODE 0  no value of the warp's threads is flagged: branch-free row loop without any sanitizer arithmetic;
+    //   MODE 1  NaN flags only (land points of a NaN-masked field: the common case): the same loop, and a flagged
+    //           point's new value is forced to NaN afterwards -- which is what -NaN - c*Lap and 2A - NaN give;
+    //   MODE 2  an inf flag somewhere: the raw values of the point-wise terms are rebuilt from the bits (selects).
+    // In every form the new values are examined after the loop and only a fresh NaN / inf among them triggers
+    // nan_to_num and the flag update of that value; the rows are published last.
+    template <bool ALLROWS, int MODE>
     GCMF_HD void step_rows_ss(int tid, int s, const T* __restrict__ S, T* __restrict__ D, T (&X1)[G::R][G::VX],
                               T (&X2)[G::R][G::VX], int a1, Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
@@ -669,6 +672,9 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         const bool publish = !GCMF_OPT_SKIPLAST || s < P.k;
         constexpr bool CONTRACT = GCMF_OPT_CONTRACT != 0;
         const int f1 = a1 * 16, f2 = (a1 ^ 1) * 16;
+        // MODE 1: points whose T_{i-1} or T_{i-2} is NaN; their T_i is NaN
+        const uint32_t force = MODE == 1 ? ((st.nanbits >> f1) | (st.nanbits >> f2)) & 0xffffu : 0u;
+        uint32_t region = 0;  // bit (q*VX+v) set for the rows this step computes
         T os[G::VX], on[G::VX];
         if (ALLROWS || lr0 > 0) Ld<T, G::VX>::go(Sc - G::TW, os);
         if (ALLROWS || lr0 + G::R < G::TH) Ld<T, G::VX>::go(Sc + G::R * G::TW, on);
@@ -681,6 +687,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                 have_prev = false;
                 continue;
             }
+            region |= ROWMASK << (q * G::VX);
             const T ow = Sw[q * G::TW];
             const T oe = Se[q * G::TW];
             const T* CE = tileC(0) + off0 + q * G::TW;
@@ -699,6 +706,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
             Ld<T, G::VX>::go(RA, ra);
 #pragma unroll
             for (int v = 0; v < G::VX; ++v) {
+                const int idx = q * G::VX + v;
                 const T o_e = v == G::VX - 1 ? oe : X1[q][v + 1 < G::VX ? v + 1 : v];
                 const T o_w = v == 0 ? ow : X1[q][v > 0 ? v - 1 : 0];
                 const T o_n = q == G::R - 1 ? on[v] : X1[q + 1 < G::R ? q + 1 : q][v];
@@ -706,36 +714,39 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                 const T lap = flux_lap<T>(X1[q][v], o_w, o_e, o_n, o_s, ce[v], v == 0 ? cew : ce[v > 0 ? v - 1 : 0],
                                           cn[v], cs[v], ra[v]);
                 T x = X1[q][v], t2 = X2[q][v];
-                if (GENERAL) {  // rebuild the raw values of the point-wise terms
-                    const int idx = q * G::VX + v;
+                if (MODE == 2) {  // rebuild the raw values of the point-wise terms
                     x = raw_of<T>(x, (st.nanbits >> (f1 + idx)) & 1u, (st.infbits >> (f1 + idx)) & 1u);
                     t2 = raw_of<T>(t2, (st.nanbits >> (f2 + idx)) & 1u, (st.infbits >> (f2 + idx)) & 1u);
                 }
                 const T a = shifted_flux<T>(x, c, lap);                  // filter.py:171
-                const T t0 = start ? a : cheb_next<T>(a, t2);            // filter.py:192-194 / 197-203
+                T t0 = start ? a : cheb_next<T>(a, t2);                  // filter.py:192-194 / 197-203
+                if (MODE == 1 && ((force >> idx) & 1u)) t0 = (T)NAN;
                 const double b0 = start ? P.p0 * (double)x : (double)st.acc[q][v];
                 st.acc[q][v] = (T)bar_update<CONTRACT>(b0, pk, (double)t0);  // filter.py:195 / 204
-                X2[q][v] = t0;                                           // raw T_i replaces T_{i-2}
+                X2[q][v] = (MODE == 1 && ((force >> idx) & 1u)) ? T(0) : t0;  // T_i replaces T_{i-2} (NaN -> 0)
                 cn_prev[v] = cn[v];
             }
             have_prev = true;
         }
-        // sanitize what has to be sanitized: nothing, unless a new value is NaN / inf (or flags have to be cleared)
-        bool nf = GENERAL;
-        if (!GENERAL) {
+        if (MODE == 1)  // the forced points are the NaNs of T_i so far; no inf bits exist in this mode
+            st.nanbits = (st.nanbits & ~(region << f2)) | ((force & region) << f2);
+        // a fresh NaN / inf among the new values (MODE 2: any value at all) gets its flags and nan_to_num
+        bool nf = MODE == 2;
+        if (MODE != 2) {
 #pragma unroll
             for (int q = 0; q < G::R; ++q)
 #pragma unroll
                 for (int v = 0; v < G::VX; ++v)
-                    if (ALLROWS || (lr0 + q >= s && lr0 + q < G::TH - s)) nf = nf || nonfinite(X2[q][v]);
+                    if ((region >> (q * G::VX + v)) & 1u) nf = nf || nonfinite(X2[q][v]);
         }
         if (nf) {
 #pragma unroll
             for (int q = 0; q < G::R; ++q) {
-                if (!ALLROWS && (lr0 + q < s || lr0 + q >= G::TH - s)) continue;
 #pragma unroll
                 for (int v = 0; v < G::VX; ++v) {
-                    const uint32_t bit = 1u << (f2 + q * G::VX + v);
+                    const int idx = q * G::VX + v;
+                    if (!((region >> idx) & 1u) || ((force >> idx) & 1u)) continue;
+                    const uint32_t bit = 1u << (f2 + idx);
                     const T t0 = X2[q][v];
                     const bool isn = t0 != t0;
                     const bool isi = !isn && nonfinite(t0);
@@ -748,7 +759,19 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         if (publish) {
 #pragma unroll
             for (int q = 0; q < G::R; ++q)
-                if (ALLROWS || (lr0 + q >= s && lr0 + q < G::TH - s)) St<T, G::VX>::go(D + off0 + q * G::TW, X2[q]);
+                if ((region >> (q * G::VX)) & 1u) St<T, G::VX>::go(D + off0 + q * G::TW, X2[q]);
+        }
+    }
+
+    template <int MODE> GCMF_HD void step_ss(int tid, int s, bool inner, Thread& st) const {
+        const T* Ssrc = (s & 1) ? tileS(0) : tileS(1);
+        T* Sdst = (s & 1) ? tileS(1) : tileS(0);
+        if (s & 1) {
+            if (inner) step_rows_ss<true, MODE>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
+            else step_rows_ss<false, MODE>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
+        } else {
+            if (inner) step_rows_ss<true, MODE>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
+            else step_rows_ss<false, MODE>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
         }
     }
 
@@ -759,27 +782,12 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         if (lc0 + G::VX <= s || lc0 >= G::TW - s) return;  // column group outside the region
         const bool inner = ty * G::R >= G::H && (ty + 1) * G::R <= G::TH - G::H;  // rows inside for every s <= H
         if (SANSTATE) {
-            // one code path per warp: the general form as soon as any of its threads holds a flagged value
-            const bool general = warp_any((st.nanbits | st.infbits) != 0u);
-            const T* Ssrc = (s & 1) ? tileS(0) : tileS(1);
-            T* Sdst = (s & 1) ? tileS(1) : tileS(0);
-            if (s & 1) {
-                if (inner) {
-                    if (general) step_rows_ss<true, true>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
-                    else step_rows_ss<true, false>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
-                } else {
-                    if (general) step_rows_ss<false, true>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
-                    else step_rows_ss<false, false>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
-                }
-            } else {
-                if (inner) {
-                    if (general) step_rows_ss<true, true>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
-                    else step_rows_ss<true, false>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
-                } else {
-                    if (general) step_rows_ss<false, true>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
-                    else step_rows_ss<false, false>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
-                }
-            }
+            // one code path per warp: as general as its most demanding thread needs
+            const bool any_inf = warp_any(st.infbits != 0u);
+            const bool any_nan = warp_any(st.nanbits != 0u);
+            if (any_inf) step_ss<2>(tid, s, inner, st);
+            else if (any_nan) step_ss<1>(tid, s, inner, st);
+            else step_ss<0>(tid, s, inner, st);
             return;
         }
         if (s & 1) {
