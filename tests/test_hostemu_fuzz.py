@@ -67,3 +67,9 @@ def test_opt_in_kernel_variants_in_emulator(defs, tmp_path):
     res = subprocess.run([sys.executable, os.path.join(here, "tools", "fuzz_hostemu.py"), "--cases", "150", "--seed", "5"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:]
+    if "-DGCMF_OPT_CONTRACT=1" not in defs:  # same roundings as the default build: bit-identical, inf paths included
+        from hostemu_util import EMU_LIB, emu_library
+        emu_library()
+        res = subprocess.run([sys.executable, os.path.join(here, "tools", "diff_variants.py"), EMU_LIB, lib,
+                              "--cases", "80", "--seed", "2"], capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0, res.stdout[-3000:]
