@@ -61,6 +61,12 @@ constexpr int FUSED_H = 4;  // halo width = max fused steps
 // (written after the round-1 GPU budget was spent); parity-test on the GPU before switching it on.
 #define GCMF_OPT_EDGEREFILL 0
 #endif
+#ifndef GCMF_OPT_STATICMASK
+// REGULAR5: "has a wet mask" is a run-time flag that the step loop tests per point, which splits the unrolled row
+// loop into ~40 small basic blocks; with the switch on the loop is instantiated twice (masked / unmasked) and the
+// flag picks one per step.  NOT YET MEASURED.
+#define GCMF_OPT_STATICMASK 0
+#endif
 #ifndef GCMF_OPT_SANSTATE
 // FLUX: keep the SANITIZED T_{i-1} / T_{i-2} in the per-thread registers, plus one NaN bit and one inf bit per
 // value, instead of the raw values.  The sanitized value is what the Laplacian differences and what is published,
@@ -265,9 +271,10 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
     GCMF_HD T* tileC(int which) const { return smem + (size_t)(4 + which) * G::PLANE; }
 
     // value published to the neighbours: what the reference's Laplacian differences
-    GCMF_HD T sanitize(T x, bool wet) const {
+    GCMF_HD T sanitize(T x, bool wet) const { return sanitize(x, wet, masked); }
+    GCMF_HD T sanitize(T x, bool wet, bool msk) const {
         if (KIND == FK_FLUX) return nan2num(x);                    // kernels.py:300, 566
-        if (masked) return wet ? nan2num(x) : T(0);                // kernels.py:175-176
+        if (msk) return wet ? nan2num(x) : T(0);                   // kernels.py:175-176
         return x;                                                  // kernels.py:113-121: NaNs spread
     }
 
@@ -519,9 +526,11 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
     // X1 holds T_{i-1} (raw), X2 holds T_{i-2}; the new T_i is written over X2, so consecutive steps just swap
     // the roles of the two register arrays (no moves).  ALLROWS: the thread's R rows all lie in the region for
     // every s <= H (its rows are core rows), which removes every branch from the row loop.
-    template <bool ALLROWS>
+    // MSK: -1 = the run-time flag `masked`, 0 / 1 = known at compile time (GCMF_OPT_STATICMASK)
+    template <bool ALLROWS, int MSK = -1>
     GCMF_HD void step_rows(int tid, int s, const T* __restrict__ S, T* __restrict__ D, T (&X1)[G::R][G::VX],
                            T (&X2)[G::R][G::VX], Thread& st) const {
+        const bool msk = MSK < 0 ? masked : MSK != 0;
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         const int lr0 = ty * G::R;
@@ -592,7 +601,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                     const T o_s = q == 0 ? os[v] : o[q > 0 ? q - 1 : 0][v];
                     const int idx = q * G::VX + v;
                     T lap;
-                    if (masked) {  // kernels.py:178-186
+                    if (msk) {  // kernels.py:178-186
                         const T wf = (T)(int)((st.wfbits >> (4 * idx)) & 0xfull);
                         const T r = (((-wf * o[q][v] + o_e) + o_w) + o_n) + o_s;
                         lap = ((st.mbits >> idx) & 1u) ? r : T(0);
@@ -622,7 +631,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                 }
             } else if (!DEFER && publish) {
 #pragma unroll
-                for (int v = 0; v < G::VX; ++v) pub[v] = sanitize(t0[v], (st.mbits >> (q * G::VX + v)) & 1u);
+                for (int v = 0; v < G::VX; ++v) pub[v] = sanitize(t0[v], (st.mbits >> (q * G::VX + v)) & 1u, msk);
                 St<T, G::VX>::go(D + off0 + q * G::TW, pub);
             }
         }
@@ -775,6 +784,16 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         }
     }
 
+    template <int MSK> GCMF_HD void step_static(int tid, int s, bool inner, Thread& st) const {
+        if (s & 1) {
+            if (inner) step_rows<true, MSK>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
+            else step_rows<false, MSK>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
+        } else {
+            if (inner) step_rows<true, MSK>(tid, s, tileS(1), tileS(0), st.t2, st.t1, st);
+            else step_rows<false, MSK>(tid, s, tileS(1), tileS(0), st.t2, st.t1, st);
+        }
+    }
+
     // odd steps read T_{i-1} from st.t1 and overwrite st.t2; even steps the other way round
     GCMF_HD void step(int tid, int s, Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
@@ -788,6 +807,11 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
             if (any_inf) step_ss<2>(tid, s, inner, st);
             else if (any_nan) step_ss<1>(tid, s, inner, st);
             else step_ss<0>(tid, s, inner, st);
+            return;
+        }
+        if (GCMF_OPT_STATICMASK && KIND == FK_REG5) {
+            if (masked) step_static<1>(tid, s, inner, st);
+            else step_static<0>(tid, s, inner, st);
             return;
         }
         if (s & 1) {
