@@ -2,11 +2,13 @@
 # Development tool for one gpurun call: time the A/B variants under build/variants against the in-tree library,
 # run the GPU test-suite on the in-tree build and, if a variant beats it by > 1.5 %, once more on that variant.
 #   gpurun -- 'sh tests/tools/ab_and_verify.sh c00c offpf2 ...'
+# VB_ARGS passes extra arguments to variant_bench.py, e.g. the cfg2-like REGULAR5 problem:
+#   VB_ARGS="--op reg5 --dtype f32 --ny 720 --nx 1440 --nb 365 --steps 11" sh tests/tools/ab_and_verify.sh sm
 V=build/variants
 ARGS="intree=gcm_filters_b200/libgcmf.so"
 for n in "$@"; do ARGS="$ARGS $n=$V/libgcmf_$n.so"; done
 mkdir -p gpurun_out
-timeout 60 python tests/tools/variant_bench.py --reps 4 $ARGS > gpurun_out/variants_final.log 2>&1
+timeout 60 python tests/tools/variant_bench.py --reps 4 ${VB_ARGS:-} $ARGS > gpurun_out/variants_final.log 2>&1
 cat gpurun_out/variants_final.log
 timeout 70 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests_intree.log 2>&1
 echo "rc=$?" >> gpurun_out/gpu_tests_intree.log

@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--steps", type=int, default=44)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--dtype", default="f64")
+    ap.add_argument("--op", default="flux", choices=["flux", "reg5"],
+                    help="flux: three coefficient planes (cfg3-like); reg5: 5-point stencil with a uint8 wet mask (cfg2-like, "
+                         "use --dtype f32 --ny 720 --nx 1440 --nb 365 --steps 11)")
     ap.add_argument("libs", nargs="+")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -38,6 +41,7 @@ def main():
     ce = (0.9 + 0.2 * torch.rand((ny, nx), generator=g, device=dev, dtype=tdt)) * wet * torch.roll(wet, -1, 1)
     cn = (0.9 + 0.2 * torch.rand((ny, nx), generator=g, device=dev, dtype=tdt)) * wet * torch.roll(wet, -1, 0)
     ra = 1.0 / (0.9 + 0.2 * torch.rand((ny, nx), generator=g, device=dev, dtype=tdt))
+    wet8 = wet.to(torch.uint8).contiguous()
     p = [1.0 / (i + 2) * (-1) ** i for i in range(args.steps + 1)]
     out = torch.empty_like(field)
     first = None
@@ -45,10 +49,15 @@ def main():
     for spec in args.libs:
         name, path = spec.split("=", 1)
         lib = _cabi.Library(os.path.abspath(path))
-        h = lib.plan_create(_cabi.OP_FLUX, _cabi.GCMF_F64 if tdt == torch.float64 else _cabi.GCMF_F32, ny, nx,
-                            _cabi.FLAG_NAN2NUM | _cabi.FLAG_WRAP_Y, 0)
-        for slot, t in enumerate((ce, cn, ra)):
-            lib.plan_set_plane(h, slot, t.data_ptr(), nx, ny * nx, 1)
+        gdt = _cabi.GCMF_F64 if tdt == torch.float64 else _cabi.GCMF_F32
+        if args.op == "flux":
+            h = lib.plan_create(_cabi.OP_FLUX, gdt, ny, nx, _cabi.FLAG_NAN2NUM | _cabi.FLAG_WRAP_Y, 0)
+            for slot, t in enumerate((ce, cn, ra)):
+                lib.plan_set_plane(h, slot, t.data_ptr(), nx, ny * nx, 1)
+        else:
+            h = lib.plan_create(_cabi.OP_REGULAR5, gdt, ny, nx,
+                                _cabi.FLAG_MASK | _cabi.FLAG_NAN2NUM | _cabi.FLAG_WRAP_Y, 0)
+            lib.plan_set_plane(h, 0, wet8.data_ptr(), nx, ny * nx, 1)
         lib.plan_set_filter(h, p, 0.1)
         wsb = lib.workspace_bytes(h, nb)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
