@@ -61,6 +61,12 @@ constexpr int FUSED_H = 4;  // halo width = max fused steps
 // (written after the round-1 GPU budget was spent); parity-test on the GPU before switching it on.
 #define GCMF_OPT_EDGEREFILL 0
 #endif
+#ifndef GCMF_OPT_ROWPTR
+// 64-bit address arithmetic of load_bar / store: one full "level * bstride + first_row * pitch + column" per array
+// and level, then + q * pitch with the unrolled q, instead of a full 64-bit multiply-add per row and array (the
+// two phases are ~270 of the ~1730 instructions a warp spends per level, mostly IMAD).  NOT YET MEASURED.
+#define GCMF_OPT_ROWPTR 0
+#endif
 #ifndef GCMF_OPT_STATICMASK
 // REGULAR5: "has a wet mask" is a run-time flag that the step loop tests per point, which splits the unrolled row
 // loop into ~40 small basic blocks; with the switch on the loop is instantiated twice (masked / unmasked) and the
@@ -436,12 +442,20 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         const bool oc = owns_cols(tx);
+#if GCMF_OPT_ROWPTR
+        const int64_t ob = level * P.bar.bstride + (int64_t)(cy0 + ty * G::R - G::H) * P.bar.pitch +
+                           (cx0 + lc0 - G::H);  // element offset of the thread's first row
+#endif
 #pragma unroll
         for (int q = 0; q < G::R; ++q) {
             const int lr = ty * G::R + q;
             if (oc && owns_row(lr) && !is_first()) {
+#if GCMF_OPT_ROWPTR
+                Ld<T, G::VX>::go(P.bar.p + (ob + (int64_t)q * P.bar.pitch), st.acc[q]);
+#else
                 Ld<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)(cy0 + lr - G::H) * P.bar.pitch +
                                      (cx0 + lc0 - G::H), st.acc[q]);
+#endif
             } else {
 #pragma unroll
                 for (int v = 0; v < G::VX; ++v) st.acc[q][v] = T(0);
@@ -829,6 +843,19 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         if (!owns_cols(tx)) return;
         const int lc0 = tx * G::VX;
         const int gx = cx0 + lc0 - G::H;
+#if GCMF_OPT_ROWPTR
+        const int gyf = cy0 + ty * G::R - G::H;  // element offsets of the thread's first row in the output arrays
+        const int64_t ob0 = level * P.bar.bstride + (int64_t)gyf * P.bar.pitch + gx;
+        const int64_t o10 = is_last() ? 0 : level * P.t1_out.bstride + (int64_t)gyf * P.t1_out.pitch + gx;
+        const int64_t o20 = is_last() ? 0 : level * P.t2_out.bstride + (int64_t)gyf * P.t2_out.pitch + gx;
+#define GCMF_BAR_ROW(q_, gy_) (P.bar.p + (ob0 + (int64_t)(q_) * P.bar.pitch))
+#define GCMF_T1_ROW(q_, gy_) (P.t1_out.p + (o10 + (int64_t)(q_) * P.t1_out.pitch))
+#define GCMF_T2_ROW(q_, gy_) (P.t2_out.p + (o20 + (int64_t)(q_) * P.t2_out.pitch))
+#else
+#define GCMF_BAR_ROW(q_, gy_) (P.bar.p + level * P.bar.bstride + (int64_t)(gy_) * P.bar.pitch + gx)
+#define GCMF_T1_ROW(q_, gy_) (P.t1_out.p + level * P.t1_out.bstride + (int64_t)(gy_) * P.t1_out.pitch + gx)
+#define GCMF_T2_ROW(q_, gy_) (P.t2_out.p + level * P.t2_out.bstride + (int64_t)(gy_) * P.t2_out.pitch + gx)
+#endif
 #pragma unroll
         for (int q = 0; q < G::R; ++q) {
             const int lr = ty * G::R + q;
@@ -857,18 +884,30 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                         n2[v] = raw_of<T>((P.k & 1) ? st.t1[q][v] : st.t2[q][v], (st.nanbits >> (fb + idx)) & 1u,
                                           (st.infbits >> (fb + idx)) & 1u);
                     }
-                    St<T, G::VX>::go(P.t1_out.p + level * P.t1_out.bstride + (int64_t)gy * P.t1_out.pitch + gx, n1);
-                    St<T, G::VX>::go(P.t2_out.p + level * P.t2_out.bstride + (int64_t)gy * P.t2_out.pitch + gx, n2);
+                    St<T, G::VX>::go(GCMF_T1_ROW(q, gy), n1);
+                    St<T, G::VX>::go(GCMF_T2_ROW(q, gy), n2);
                 } else {
-                St<T, G::VX>::go(P.t1_out.p + level * P.t1_out.bstride + (int64_t)gy * P.t1_out.pitch + gx,
-                                 (P.k & 1) ? st.t2[q] : st.t1[q]);
-                St<T, G::VX>::go(P.t2_out.p + level * P.t2_out.bstride + (int64_t)gy * P.t2_out.pitch + gx,
-                                 (P.k & 1) ? st.t1[q] : st.t2[q]);
+#if GCMF_OPT_ROWPTR
+                T n1[G::VX], n2[G::VX];  // value selects: a select between the two register arrays themselves can
+#pragma unroll                           // push the whole per-thread state into local memory
+                for (int v = 0; v < G::VX; ++v) {
+                    n1[v] = (P.k & 1) ? st.t2[q][v] : st.t1[q][v];
+                    n2[v] = (P.k & 1) ? st.t1[q][v] : st.t2[q][v];
+                }
+                St<T, G::VX>::go(GCMF_T1_ROW(q, gy), n1);
+                St<T, G::VX>::go(GCMF_T2_ROW(q, gy), n2);
+#else
+                St<T, G::VX>::go(GCMF_T1_ROW(q, gy), (P.k & 1) ? st.t2[q] : st.t1[q]);
+                St<T, G::VX>::go(GCMF_T2_ROW(q, gy), (P.k & 1) ? st.t1[q] : st.t2[q]);
+#endif
                 }
             }
-            St<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)gy * P.bar.pitch + gx, outv);
+            St<T, G::VX>::go(GCMF_BAR_ROW(q, gy), outv);
         }
     }
+#undef GCMF_BAR_ROW
+#undef GCMF_T1_ROW
+#undef GCMF_T2_ROW
 };
 
 #ifdef __CUDACC__
