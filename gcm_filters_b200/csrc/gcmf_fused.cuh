@@ -897,8 +897,21 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                 St<T, G::VX>::go(GCMF_T1_ROW(q, gy), n1);
                 St<T, G::VX>::go(GCMF_T2_ROW(q, gy), n2);
 #else
+                if (KIND == FK_REG5) {
+                    // value selects: ptxas -v showed a 128-byte stack frame for fused_kernel<double, REG5> -- the
+                    // select between the two register arrays below had pushed t1 / t2 / acc into local memory
+                    T n1[G::VX], n2[G::VX];
+#pragma unroll
+                    for (int v = 0; v < G::VX; ++v) {
+                        n1[v] = (P.k & 1) ? st.t2[q][v] : st.t1[q][v];
+                        n2[v] = (P.k & 1) ? st.t1[q][v] : st.t2[q][v];
+                    }
+                    St<T, G::VX>::go(GCMF_T1_ROW(q, gy), n1);
+                    St<T, G::VX>::go(GCMF_T2_ROW(q, gy), n2);
+                } else {
                 St<T, G::VX>::go(GCMF_T1_ROW(q, gy), (P.k & 1) ? st.t2[q] : st.t1[q]);
                 St<T, G::VX>::go(GCMF_T2_ROW(q, gy), (P.k & 1) ? st.t1[q] : st.t2[q]);
+                }
 #endif
                 }
             }
