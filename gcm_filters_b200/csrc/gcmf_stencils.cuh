@@ -521,7 +521,11 @@ GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&l
 // Same expressions, same order as OpVectorC::apply (bit-identical results), one third of the stress work.
 // =====================================================================================
 template <typename T> struct CgridTile {
-    static constexpr int TX = 32, TY = 8;               // output points per CTA
+#ifndef GCMF_CGRID_TX
+#define GCMF_CGRID_TX 32  // tile geometry: A/B knobs (tests/tools/build_variant.py -DGCMF_CGRID_TX=.. -DGCMF_CGRID_TY=..);
+#define GCMF_CGRID_TY 8   // 33 x 9 = 297 stress entries for 256 threads: the second pass of stage A runs 41 lanes
+#endif
+    static constexpr int TX = GCMF_CGRID_TX, TY = GCMF_CGRID_TY;  // output points per CTA
     static constexpr int SW = TX + 1, SH = TY + 1;      // stress tiles: one extra column / row
     static constexpr int NTHREADS = TX * TY;
     static constexpr int SMEM_ELEMS = 4 * SW * SH;
