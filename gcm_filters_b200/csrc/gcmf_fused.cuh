@@ -89,14 +89,6 @@ constexpr int FUSED_H = 4;  // halo width = max fused steps
 // sanitizer is a third of the step loop's instructions.  Same results by construction.  NOT YET MEASURED.
 #define GCMF_OPT_ROWNAN 0
 #endif
-#ifndef GCMF_OPT_LATEWAIT
-// FLUX: drop the neighbour wait in front of `extract` when the block has an even number of steps.  extract only
-// writes the thread's own points of work tile S0; the neighbours' last step k reads S[(k-1)&1] = S1 for even k, so
-// nothing they still read is touched, and having run its own step k this warp already knows that they finished
-// step k-1 (the last reader of S0).  Step 1 of the new level still waits for the neighbours' extract.  One more
-// phase of drift between neighbouring warps.  NOT YET MEASURED / GPU-tested (see GCMF_OPT_EDGEREFILL).
-#define GCMF_OPT_LATEWAIT 0
-#endif
 
 // XS: how the tile row is split over threads.  1: one 16-byte vector per thread and row (512 threads, used by
 // the register-heavy FLUX kernel); 2: half a vector (1024 threads: the light REGULAR5 steps hide their latency
@@ -1031,7 +1023,10 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
         tl.load_bar(tid, l, st);
         if (KIND == FK_FLUX && it == 0) mbar_wait(&mb[0], 0);
         mbar_wait(&mb[1], (unsigned)(it & 1));
-        if (!(GCMF_OPT_LATEWAIT && (P.k & 1) == 0)) wait_neighbours(g0);
+        // (Dropping this wait for even k -- extract only writes the thread's own points of S0, which no neighbour
+        // reads after step k-1 -- is NOT safe: a neighbour could then arrive for phase g+2 on a barrier whose phase g
+        // is still open, and the counting barrier cannot tell the two apart.  tests/tools/sync_model.py --latewait.)
+        wait_neighbours(g0);
         tl.extract(tid, st);
         publish(g0 + 1);
         // The landing tiles are refilled for the next level once every warp has drained them (32 lanes = TH rows).

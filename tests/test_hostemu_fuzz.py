@@ -73,3 +73,24 @@ def test_opt_in_kernel_variants_in_emulator(defs, tmp_path):
         res = subprocess.run([sys.executable, os.path.join(here, "tools", "diff_variants.py"), EMU_LIB, lib,
                               "--cases", "80", "--seed", "2"], capture_output=True, text=True, timeout=900)
         assert res.returncode == 0, res.stdout[-3000:]
+
+
+def test_neighbour_barrier_protocol_model():
+    """tests/tools/sync_model.py: the mbarrier protocol of fused_kernel<FLUX> (and its EDGEREFILL variant) under
+    random skewed schedules -- no stale or overwritten tile rows, no deadlock; the rejected LATEWAIT relaxation must
+    be caught (so the checker is known to bite)."""
+    import random
+    import sync_model
+    rng = random.Random(5)
+    for edge in (0, 1):
+        for skip in (0, 1):
+            for k in (1, 2, 3, 4):
+                for _ in range(12):
+                    sync_model.Model(k, 3, edge, 0, skip, rng).run()
+    caught = 0
+    for _ in range(40):
+        try:
+            sync_model.Model(4, 3, 0, 1, 0, rng).run()
+        except sync_model.Violation:
+            caught += 1
+    assert caught > 0
