@@ -180,3 +180,23 @@ def test_c_abi_from_plain_c(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "arch=100" in res.stdout and "unknown op 99" in res.stdout and res.stdout.strip().endswith("ok")
+
+
+def test_c_driver_of_the_abi_against_the_emulator(tmp_path):
+    """tests/cabi/gpu_vs_emu.c in its --emu-only mode (emulator against itself): keeps the plain-C GPU checker
+    building and its nine cases running; on a GPU box the same binary compares libgcmf.so with the emulator."""
+    import shutil
+    import subprocess
+    import sys
+    cuda_inc = "/usr/local/cuda/include"
+    if shutil.which("gcc") is None or not os.path.isfile(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("needs gcc and the CUDA runtime headers")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from hostemu_util import emu_library
+    emu_library()
+    exe = str(tmp_path / "gpu_vs_emu")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "tests", "cabi", "gpu_vs_emu.c"),
+                    "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, "-L", "/usr/local/cuda/lib64",
+                    "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart", "-ldl", "-lm", "-o", exe], check=True)
+    res = subprocess.run([exe, "--emu-only"], cwd=ROOT, capture_output=True, text=True)
+    assert res.returncode == 0 and "all cases bit-identical" in res.stdout, res.stdout + res.stderr
