@@ -6,6 +6,7 @@
  *       -Wl,-rpath,/usr/local/cuda/lib64 -lcudart -ldl -lm -o tests/cabi/gpu_vs_emu
  *   ./tests/cabi/gpu_vs_emu            (on a GPU box, from the repository root)
  *   ./tests/cabi/gpu_vs_emu --emu-only (anywhere: emulator against itself, checks this program)
+ *   ./tests/cabi/gpu_vs_emu build/variants/libgcmf_ss.so [emulator.so]   (an A/B variant: 3 s instead of a pytest run)
  *
  * Cases: the kernels whose device code changed after the last full GPU run of round 1 -- the tiled C-grid kernel
  * (grids narrower than a tile, odd sizes) and the fused REGULAR5 kernel (whole grid and latitude band with ghost
@@ -214,10 +215,13 @@ static int compare(const char* name, int dtype, const void* x, const void* y, si
 
 int main(int argc, char** argv) {
     const int emu_only = argc > 1 && !strcmp(argv[1], "--emu-only");
+    /* optional: the CUDA library under test (e.g. an A/B variant from build/variants) and the emulator to compare with */
+    const char* gpu_path = (argc > 1 && !emu_only) ? argv[1] : "gcm_filters_b200/libgcmf.so";
+    const char* emu_path = (argc > 2 && !emu_only) ? argv[2] : "tests/hostemu/libgcmf_hostemu.so";
     Api gpu, emu;
     int bad = 0, c;
-    if (load(&emu, "tests/hostemu/libgcmf_hostemu.so", 0)) return 2;
-    if (load(&gpu, emu_only ? "tests/hostemu/libgcmf_hostemu.so" : "gcm_filters_b200/libgcmf.so", !emu_only)) return 2;
+    if (load(&emu, emu_path, 0)) return 2;
+    if (load(&gpu, emu_only ? emu_path : gpu_path, !emu_only)) return 2;
     printf("library under test: sm_arch %d%s\n", gpu.sm_arch(), emu_only ? " (emulator against itself)" : "");
     if (!emu_only && cudaSetDevice(0) != cudaSuccess) {
         fprintf(stderr, "no CUDA device\n");

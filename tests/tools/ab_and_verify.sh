@@ -5,9 +5,17 @@
 # VB_ARGS passes extra arguments to variant_bench.py, e.g. the cfg2-like REGULAR5 problem:
 #   VB_ARGS="--op reg5 --dtype f32 --ny 720 --nx 1440 --nb 365 --steps 11" sh tests/tools/ab_and_verify.sh sm
 V=build/variants
+mkdir -p gpurun_out
 ARGS="intree=gcm_filters_b200/libgcmf.so"
 for n in "$@"; do ARGS="$ARGS $n=$V/libgcmf_$n.so"; done
-mkdir -p gpurun_out
+# 3-second plain-C check of every variant against the host emulator first (bit-identical expected for all switches but
+# CONTRACT): a variant that fails here is dropped from the timing
+if [ -x tests/cabi/gpu_vs_emu ]; then
+    for n in "$@"; do
+        ./tests/cabi/gpu_vs_emu "$V/libgcmf_$n.so" > "gpurun_out/gpu_vs_emu_$n.log" 2>&1 || echo "variant $n: differs from the emulator (see gpurun_out/gpu_vs_emu_$n.log)"
+        tail -n 1 "gpurun_out/gpu_vs_emu_$n.log"
+    done
+fi
 timeout 60 python tests/tools/variant_bench.py --reps 4 ${VB_ARGS:-} $ARGS > gpurun_out/variants_final.log 2>&1
 cat gpurun_out/variants_final.log
 timeout 70 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests_intree.log 2>&1
