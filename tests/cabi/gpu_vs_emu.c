@@ -144,8 +144,6 @@ static double run(const Api* a, int op, int dtype, int ny, int nx, int flags, in
         void* ws;
         void* zero = calloc(1, fbytes);
         CHECK(a, a->ws_bytes(plan, nb, &wsb));
-        ws = to_side(a, NULL, 0);
-        free_side(a, ws);
         if (a->device) {
             if (cudaMalloc(&ws, wsb ? wsb : 256) != cudaSuccess) return -1.0;
         } else if (posix_memalign(&ws, 256, wsb ? wsb : 256)) {
