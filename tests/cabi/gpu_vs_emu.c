@@ -8,9 +8,9 @@
  *   ./tests/cabi/gpu_vs_emu --emu-only (anywhere: emulator against itself, checks this program)
  *   ./tests/cabi/gpu_vs_emu build/variants/libgcmf_ss.so [emulator.so]   (an A/B variant: 3 s instead of a pytest run)
  *
- * Cases: the kernels whose device code changed after the last full GPU run of round 1 -- the tiled C-grid kernel
- * (grids narrower than a tile, odd sizes) and the fused REGULAR5 kernel (whole grid and latitude band with ghost
- * rows) -- plus one fused flux case as a control.
+ * Cases: every operator family, one-step and fused kernels, whole grids, tripolar folds and latitude bands with ghost
+ * rows, fp32 and fp64 (the first nine are the ones run on a B200 at the end of round 1, profiles/gpu_vs_emu_r01.log:
+ * the kernels whose device code had changed after the last full GPU test run).
  */
 #define _POSIX_C_SOURCE 200112L
 #include <dlfcn.h>
@@ -239,13 +239,25 @@ int main(int argc, char** argv) {
         {"reg5 masked f64 band 40(+8)x264", GCMF_OP_REGULAR5, GCMF_F64, 40, 264, GCMF_FLAG_MASK | GCMF_FLAG_NAN2NUM, 4, 2, 9},
         {"reg5 masked f32 band 36(+8)x264", GCMF_OP_REGULAR5, GCMF_F32, 36, 264, GCMF_FLAG_MASK | GCMF_FLAG_NAN2NUM, 4, 2, 9},
         {"flux f64 48x256 fused (control)", GCMF_OP_FLUX, GCMF_F64, 48, 256, GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM, 0, 2, 9},
+        {"flux f32 40x264 fused", GCMF_OP_FLUX, GCMF_F32, 40, 264, GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM, 0, 3, 10},
+        {"flux f64 48x256 fused, tripolar fold", GCMF_OP_FLUX, GCMF_F64, 48, 256,
+         GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM | GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S, 0, 2, 9},
+        {"flux f64 37x54 one-step (odd)", GCMF_OP_FLUX, GCMF_F64, 37, 54, GCMF_FLAG_WRAP_Y | GCMF_FLAG_NAN2NUM, 0, 2, 7},
+        {"flux f64 band 40(+8)x256 fused", GCMF_OP_FLUX, GCMF_F64, 40, 256, GCMF_FLAG_NAN2NUM, 4, 2, 9},
+        {"vector B f64 37x54", GCMF_OP_VECTOR_B, GCMF_F64, 37, 54, GCMF_FLAG_WRAP_Y, 0, 2, 6},
+        {"vector B f32 33x64", GCMF_OP_VECTOR_B, GCMF_F32, 33, 64, GCMF_FLAG_WRAP_Y, 0, 1, 5},
+        {"reg5 masked+area f64 40x264 fused", GCMF_OP_REGULAR5, GCMF_F64, 40, 264,
+         GCMF_FLAG_WRAP_Y | GCMF_FLAG_MASK | GCMF_FLAG_NAN2NUM | GCMF_FLAG_AREA, 0, 2, 9},
+        {"reg5 masked f64 40x264 tripolar fused", GCMF_OP_REGULAR5, GCMF_F64, 40, 264,
+         GCMF_FLAG_WRAP_Y | GCMF_FLAG_MASK | GCMF_FLAG_NAN2NUM | GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S, 0, 2, 9},
     };
     for (c = 0; c < (int)(sizeof cases / sizeof cases[0]); ++c) {
         const int op = cases[c].op, dt = cases[c].dtype, ny = cases[c].ny, nx = cases[c].nx, gh = cases[c].ghost;
         const int nb = cases[c].nb, nya = ny + 2 * gh;
         const size_t es = dt == GCMF_F64 ? 8 : 4, npl = (size_t)nya * nx, nf = (size_t)nb * npl;
-        const int ncomp = op == GCMF_OP_VECTOR_C ? 2 : 1;
-        const int nplanes = op == GCMF_OP_VECTOR_C ? 14 : (op == GCMF_OP_FLUX ? 3 : ((cases[c].flags & GCMF_FLAG_MASK) ? 1 : 0));
+        const int ncomp = (op == GCMF_OP_VECTOR_C || op == GCMF_OP_VECTOR_B) ? 2 : 1;
+        const int nplanes = op == GCMF_OP_VECTOR_C ? 14 : op == GCMF_OP_VECTOR_B ? 8 : op == GCMF_OP_FLUX ? 3
+                            : (cases[c].flags & GCMF_FLAG_AREA) ? 2 : ((cases[c].flags & GCMF_FLAG_MASK) ? 1 : 0);
         void* planes[16] = {0};
         int is_mask[16] = {0};
         void* fields[2] = {0};
@@ -254,9 +266,12 @@ int main(int argc, char** argv) {
         size_t b1 = 0, b2 = 0, i;
         int s, k;
         for (s = 0; s < nplanes; ++s) {
-            if (op == GCMF_OP_REGULAR5) {
+            if (op == GCMF_OP_REGULAR5 && s == 0) {
+                if (!(cases[c].flags & GCMF_FLAG_MASK)) continue; /* slot 0 unused without a mask */
                 mask = (unsigned char*)malloc(npl);
                 for (i = 0; i < npl; ++i) mask[i] = urand() > 0.25;
+                if (cases[c].flags & GCMF_FLAG_CUT_S)
+                    for (i = 0; i < (size_t)nx; ++i) mask[i] = 0; /* tripolar grids: row 0 is land */
                 planes[s] = mask;
                 is_mask[s] = 1;
             } else {
@@ -274,6 +289,7 @@ int main(int argc, char** argv) {
             for (i = 0; i < nf; ++i) {
                 double v = urand();
                 if (mask && !mask[i % npl]) v = NAN; /* NaN on land */
+                if (op == GCMF_OP_FLUX && urand() < 0.05) v = urand() < 0.8 ? NAN : INFINITY; /* nan_to_num at work */
                 if (dt == GCMF_F64) ((double*)fields[k])[i] = v;
                 else ((float*)fields[k])[i] = (float)v;
             }
