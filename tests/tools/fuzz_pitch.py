@@ -50,7 +50,7 @@ def unpad(view, nb, ny, nx, pitch, bstride):
     return out
 
 
-def run(lib, lap, dtype, ny, nx, fields, p, c, rng, pad, spb):
+def run(lib, lap, dtype, ny, nx, fields, p, c, rng, pad, spb, what="filter"):
     spec = lap._planes
     h = lib.plan_create(spec.op, _DT[np.dtype(dtype)], ny, nx, spec.flags, 0)
     keep = []
@@ -90,7 +90,14 @@ def run(lib, lap, dtype, ny, nx, fields, p, c, rng, pad, spb):
     nbytes = lib.workspace_bytes(h, nb)
     raw = np.zeros(nbytes + 256, dtype=np.uint8)
     off = (-raw.ctypes.data) % 256
-    lib.filter(h, nb, fin, fout, raw.ctypes.data + off, nbytes)
+    if what == "filter":
+        lib.filter(h, nb, fin, fout, raw.ctypes.data + off, nbytes)
+    elif what == "laplacian":
+        lib.laplacian(h, nb, fin, fout)
+    elif what == "prepare":
+        lib.prepare(h, nb, fin, fout)
+    else:
+        lib.finalize(h, nb, fin, fout)
     lib.plan_destroy(h)
     if pad:
         for (buf, off), pi, bs in views:  # nothing outside the (nb, ny, nx) elements of an output may be written
@@ -133,6 +140,13 @@ def one_case(rng, k):
     ref, _k1 = run(lib, lap, dtype, ny, nx, fb, spec.p, c, rng, False, spb)
     got, keep = run(lib, lap, dtype, ny, nx, fb, spec.p, c, rng, True, spb)
     desc = f"#{k} {g} {ny}x{nx} nb={nb} {np.dtype(dtype).name} n_steps={n_steps} spb={spb}"
+    # the other entry points of the boundary: one Laplacian, and the area prepare / finalize of the operator protocol
+    for what in ("laplacian",) + (("prepare", "finalize") if len(fb) == 1 else ()):
+        r1, _ = run(lib, lap, dtype, ny, nx, fb, spec.p, c, rng, False, spb, what)
+        r2, _ = run(lib, lap, dtype, ny, nx, fb, spec.p, c, rng, True, spb, what)
+        for a, b in zip(r2, r1):
+            if not np.array_equal(a, b, equal_nan=True):
+                return desc + f" strided {what} differs from the contiguous one"
     for a, b in zip(got, ref):
         if g.startswith("TRIPOLAR"):
             # strided planes / fields may take the one-step kernels where the contiguous call is fused; across a
