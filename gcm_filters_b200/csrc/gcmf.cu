@@ -746,11 +746,15 @@ template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, 
 template <typename T, int KIND, int EDGE>
 static int launch_fused_kernel_t(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
     using G = FusedGeom<T, FusedSplit<KIND>::value>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device property of the function: a process that
+    // filters on several devices (tensors on cuda:0 and cuda:1) has to set it on each of them
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         CUDA_TRY(cudaFuncSetAttribute(fused_kernel<T, KIND, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)G::smem_bytes(KIND)));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     fused_kernel<T, KIND, EDGE><<<(unsigned)ncta, G::NTHREADS, G::smem_bytes(KIND), st>>>(P);
     gcmf_count_launch(1);
