@@ -10,6 +10,11 @@ ARGS="intree=gcm_filters_b200/libgcmf.so"
 for n in "$@"; do ARGS="$ARGS $n=$V/libgcmf_$n.so"; done
 # 3-second plain-C check of every variant against the host emulator first (bit-identical expected for all switches but
 # CONTRACT): a variant that fails here is dropped from the timing
+if [ ! -x tests/cabi/gpu_vs_emu ]; then
+    gcc -std=c99 -O1 tests/cabi/gpu_vs_emu.c -I include -I /usr/local/cuda/include -L /usr/local/cuda/lib64 \
+        -Wl,-rpath,/usr/local/cuda/lib64 -lcudart -ldl -lm -o tests/cabi/gpu_vs_emu
+fi
+[ -f tests/hostemu/libgcmf_hostemu.so ] || sh tests/hostemu/build.sh
 if [ -x tests/cabi/gpu_vs_emu ]; then
     for n in "$@"; do
         ./tests/cabi/gpu_vs_emu "$V/libgcmf_$n.so" > "gpurun_out/gpu_vs_emu_$n.log" 2>&1 || echo "variant $n: differs from the emulator (see gpurun_out/gpu_vs_emu_$n.log)"
