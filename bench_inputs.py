@@ -94,11 +94,18 @@ def vector_fixture(grid_type, shape=(128, 256)):
 # ``nb`` lets callers build a bounded sample (fewer batch slices) of the same workload; the
 # 2-D planes never depend on nb.
 # ------------------------------------------------------------------------------------------
-def _batched(shape2d, nb, seed, dtype):
-    rng = Generator(PCG64(seed))
+def _batched(shape2d, nb, seed, dtype, levels=None):
+    """Uniform (nb, ny, nx) field.  ``levels=(a, b)``: only slices a..b-1 of that same field (what one rank of a
+    batch-sharded run needs): the PCG64 stream is advanced past the first ``a`` slices -- ``random`` draws one
+    64-bit word per double -- so every rank sees exactly the values of the whole array."""
+    bg = PCG64(seed)
+    rng = Generator(bg)
     if nb is None:
         return rng.random(shape2d).astype(dtype, copy=False)
-    return rng.random((nb,) + tuple(shape2d)).astype(dtype, copy=False)
+    a, b = (0, nb) if levels is None else levels
+    if a:
+        bg.advance(a * int(np.prod(shape2d)))
+    return rng.random((b - a,) + tuple(shape2d)).astype(dtype, copy=False)
 
 
 def cfg1(shape=(256, 512)):
@@ -107,9 +114,9 @@ def cfg1(shape=(256, 512)):
                 filter_args=dict(filter_scale=4.0, dx_min=1.0, filter_shape="GAUSSIAN"))
 
 
-def cfg2(nb=365, shape=(720, 1440), nan_land=True):
+def cfg2(nb=365, shape=(720, 1440), nan_land=True, levels=None):
     """REGULAR_WITH_LAND Gaussian scale 10 on a 1/4 deg fp32 field x nb daily steps (n_steps 11)."""
-    f = _batched(shape, nb, 200, np.float32)
+    f = _batched(shape, nb, 200, np.float32, levels)
     m = land_mask(shape, np.float32)
     if nan_land:
         f[..., m == 0] = np.nan
@@ -129,12 +136,12 @@ def irregular_planes(shape, dtype=np.float64):
     return gv
 
 
-def cfg3(nb=62, shape=(2400, 3600), dtype=np.float64, gaussian=True, nan_land=True):
+def cfg3(nb=62, shape=(2400, 3600), dtype=np.float64, gaussian=True, nan_land=True, levels=None):
     """IRREGULAR_WITH_LAND on a POP 0.1 deg grid x nb levels.
 
     gaussian=True: the north-star headline (GAUSSIAN filter_scale 36, dx_min 0.9 -> n_steps 44);
     gaussian=False: BASELINE configs[2] (TAPER filter_scale 9 -> n_steps 39)."""
-    f = _batched(shape, nb, 300, dtype)
+    f = _batched(shape, nb, 300, dtype, levels)
     gv = irregular_planes(shape, dtype)
     if nan_land:
         f[..., gv["wet_mask"] == 0] = np.nan
@@ -143,9 +150,9 @@ def cfg3(nb=62, shape=(2400, 3600), dtype=np.float64, gaussian=True, nan_land=Tr
     return dict(name="cfg3", grid_type="IRREGULAR_WITH_LAND", fields=(f,), grid_vars=gv, filter_args=fa)
 
 
-def cfg4(nb=None, shape=(2400, 3600)):
+def cfg4(nb=None, shape=(2400, 3600), levels=None):
     """TRIPOLAR_POP_WITH_LAND Gaussian, fp64, fold-symmetric dxn/dyn (n_steps 44)."""
-    f = _batched(shape, nb, 400, np.float64)
+    f = _batched(shape, nb, 400, np.float64, levels)
     gv = {"wet_mask": land_mask(shape)}
     gv["dxe"] = metric(shape, 1)
     gv["dye"] = metric(shape, 2)

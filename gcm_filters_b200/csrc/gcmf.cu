@@ -10,6 +10,7 @@
 #ifdef GCMF_HOSTEMU
 #define GCMF_HD inline
 #else
+#include <cuda.h>  // CUtensorMap types only: cuTensorMapEncodeTiled is resolved at run time, libcuda is not linked
 #include <cuda_runtime.h>
 #endif
 
@@ -102,6 +103,7 @@ extern "C" int gcmf_plan_create(const gcmf_plan_desc* d, gcmf_plan** out) {
     p->n_steps = 0;
     p->c = 0.0;
     p->steps_per_block = 0;
+    for (auto& m : p->coef_maps) m.p = nullptr;
 #ifdef GCMF_HOSTEMU
     p->sm_count = 1;
 #else
@@ -720,14 +722,14 @@ template <typename T, int KIND, int EDGE> static void fused_host_t(const FusedPa
         for (auto& v : smem) v = T(12345);
         FusedTile<T, KIND, EDGE> tl(P, tile, smem.data());
         for (int r = 0; r < G::TH; ++r) {
-            if (KIND == FK_FLUX) tl.issue_coef_row(r, nullptr);
-            tl.issue_state_row(r, l0, nullptr);
+            if (KIND == FK_FLUX) tl.issue_coef(r, nullptr);
+            tl.issue_state(r, l0, nullptr);
         }
         for (int t = 0; t < G::NTHREADS; ++t) tl.load_mask(t, st[t]);
         for (int64_t l = l0; l < l1; ++l) {
             for (int t = 0; t < G::NTHREADS; ++t) tl.load_bar(t, l, st[t]);
             for (int t = 0; t < G::NTHREADS; ++t) tl.extract(t, st[t]);
-            if (l + 1 < l1) for (int r = 0; r < G::TH; ++r) tl.issue_state_row(r, l + 1, nullptr);
+            if (l + 1 < l1) for (int r = 0; r < G::TH; ++r) tl.issue_state(r, l + 1, nullptr);
             for (int s = 1; s <= P.k; ++s)
                 for (int t = 0; t < G::NTHREADS; ++t) tl.step(t, s, st[t]);
             for (int t = 0; t < G::NTHREADS; ++t) tl.store(t, l, st[t]);
@@ -743,8 +745,91 @@ template <typename T, int KIND> static void fused_host(const FusedParams<T>& P, 
     }
 }
 #else
+// ---- tensor maps (TMA descriptors) of whole-tile boxes -------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc) && alignof(CUtensorMap) <= alignof(TmaDesc), "TmaDesc mirrors CUtensorMap");
+
+static EncodeTiledFn tensor_map_encoder() {
+    static const EncodeTiledFn fn = [] {
+        if (getenv("GCMF_NO_TMAP")) return (EncodeTiledFn) nullptr;  // A/B and test knob: row-wise bulk copies everywhere
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// (nx, ny[, nb]) view of an array with boxes of one tile (tw x th x 1).  False when the array cannot be described
+// (the kernel then stages that tile row by row, as it does next to the periodic boundaries).
+template <typename T>
+static bool encode_tile_map(TmaDesc* out, const void* base, int nx, int ny, int64_t nb, int64_t pitch, int64_t bstride,
+                            int tw, int th) {
+    const EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    if (nb > 1 && bstride < (int64_t)ny * pitch) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)(nb > 0 ? nb : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(T),
+                                   (cuuint64_t)(nb > 1 ? bstride : (int64_t)ny * pitch) * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)tw, (cuuint32_t)th, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const cuuint32_t rank = nb > 0 ? 3u : 2u;
+    return enc(reinterpret_cast<CUtensorMap*>(out), dt, rank, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T, int KIND>
+static const TmaDesc* state_map(gcmf_plan* pl, const FieldRef<const T>& f, int64_t nb) {
+    using G = FusedGeom<T, FusedSplit<KIND>::value>;
+    for (auto& m : pl->state_maps)
+        if (m.p == f.p && m.pitch == f.pitch && m.bstride == f.bstride && m.nb == nb) return &m.d;
+    gcmf_plan::MapEntry e{f.p, f.pitch, f.bstride, nb, {}};
+    if (!encode_tile_map<T>(&e.d, f.p, pl->desc.nx, pl->desc.ny, nb, f.pitch, f.bstride, G::TW, G::TH)) return nullptr;
+    if (pl->state_maps.size() >= 8) pl->state_maps.erase(pl->state_maps.begin());
+    pl->state_maps.push_back(e);
+    return &pl->state_maps.back().d;
+}
+
+// Fill the launch's descriptor block.  Only whole (periodic / tripolar) grids use tensor maps; inside them only the
+// tiles that touch no boundary (91 % of the tiles of a 2400 x 3600 grid) -- the kernel decides per tile.
+template <typename T, int KIND> static void make_maps(gcmf_plan* pl, const FusedParams<T>& P, FusedMaps& M) {
+    using G = FusedGeom<T, FusedSplit<KIND>::value>;
+    memset(&M, 0, sizeof M);
+    if (!(P.g.flags & FL_WRAP_Y) || !tensor_map_encoder()) return;
+    const TmaDesc* d1 = state_map<T, KIND>(pl, P.t1_in, P.nb);
+    const TmaDesc* d2 = P.first ? d1 : state_map<T, KIND>(pl, P.t2_in, P.nb);
+    d1 = state_map<T, KIND>(pl, P.t1_in, P.nb);  // (the second look-up may have evicted / moved the first entry)
+    if (d1 && d2) {
+        M.t1 = *d1;
+        M.t2 = *d2;
+        M.use |= TMAP_STATE;
+    }
+    if (KIND == FK_FLUX) {
+        bool ok = true;
+        for (int s = 0; s < 3 && ok; ++s) {
+            gcmf_plan::MapEntry& e = pl->coef_maps[s];
+            if (e.p != P.plane[s].p || e.pitch != P.plane[s].pitch) {
+                e.p = nullptr;
+                ok = encode_tile_map<T>(&e.d, P.plane[s].p, pl->desc.nx, pl->desc.ny, 0, P.plane[s].pitch, 0, G::TW, G::TH);
+                if (ok) {
+                    e.p = P.plane[s].p;
+                    e.pitch = P.plane[s].pitch;
+                }
+            }
+            if (ok) M.coef[s] = e.d;
+        }
+        if (ok) M.use |= TMAP_COEF;
+    }
+}
+
 template <typename T, int KIND, int EDGE>
-static int launch_fused_kernel_t(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
+static int launch_fused_kernel_t(gcmf_plan* pl, const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
     using G = FusedGeom<T, FusedSplit<KIND>::value>;
     // the opt-in to > 48 KB of dynamic shared memory is a per-device property of the function: a process that
     // filters on several devices (tensors on cuda:0 and cuda:1) has to set it on each of them
@@ -756,23 +841,26 @@ static int launch_fused_kernel_t(const FusedParams<T>& P, int64_t ncta, cudaStre
                                       (int)G::smem_bytes(KIND)));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    fused_kernel<T, KIND, EDGE><<<(unsigned)ncta, G::NTHREADS, G::smem_bytes(KIND), st>>>(P);
+    FusedMaps M;
+    make_maps<T, KIND>(pl, P, M);
+    fused_kernel<T, KIND, EDGE><<<(unsigned)ncta, G::NTHREADS, G::smem_bytes(KIND), st>>>(P, M);
     gcmf_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return GCMF_OK;
 }
-template <typename T, int KIND> static int launch_fused_kernel(const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
+template <typename T, int KIND>
+static int launch_fused_kernel(gcmf_plan* pl, const FusedParams<T>& P, int64_t ncta, cudaStream_t st) {
     switch ((P.first ? 1 : 0) | (P.last ? 2 : 0)) {
-        case 0: return launch_fused_kernel_t<T, KIND, 0>(P, ncta, st);
-        case 1: return launch_fused_kernel_t<T, KIND, 1>(P, ncta, st);
-        case 2: return launch_fused_kernel_t<T, KIND, 2>(P, ncta, st);
+        case 0: return launch_fused_kernel_t<T, KIND, 0>(pl, P, ncta, st);
+        case 1: return launch_fused_kernel_t<T, KIND, 1>(pl, P, ncta, st);
+        case 2: return launch_fused_kernel_t<T, KIND, 2>(pl, P, ncta, st);
     }
-    return launch_fused_kernel_t<T, KIND, 3>(P, ncta, st);
+    return launch_fused_kernel_t<T, KIND, 3>(pl, P, ncta, st);
 }
 #endif
 
 template <typename T>
-static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const gcmf_field* t1, const gcmf_field* t2,
+static int run_fused_t(gcmf_plan* pl, int64_t nb, int step0, int k, const gcmf_field* t1, const gcmf_field* t2,
                        const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st) {
     using G = FusedGeom<T>;
     const int kind = fused_kind_t<T>(pl);
@@ -838,8 +926,8 @@ static int run_fused_t(const gcmf_plan* pl, int64_t nb, int step0, int k, const 
     gcmf_count_launch(1);
     return GCMF_OK;
 #else
-    if (kind == FK_FLUX) return launch_fused_kernel<T, FK_FLUX>(P, ncta, st);
-    return launch_fused_kernel<T, FK_REG5>(P, ncta, st);
+    if (kind == FK_FLUX) return launch_fused_kernel<T, FK_FLUX>(pl, P, ncta, st);
+    return launch_fused_kernel<T, FK_REG5>(pl, P, ncta, st);
 #endif
 }
 

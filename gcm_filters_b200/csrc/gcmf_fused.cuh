@@ -36,58 +36,20 @@ enum : int { FK_FLUX = 0, FK_REG5 = 1 };
 
 constexpr int FUSED_H = 4;  // halo width = max fused steps
 
-// Compile-time switches of the fused kernels, each A/B-measured with tests/tools/build_variant.py + variant_bench.py
-// (cfg3 shape, 62 x 2400 x 3600 fp64, 44 steps, ms per filter call; profiles/variants_r01.md).  The FLUX kernel sits
-// at the 128-register cap of a 512-thread CTA, so anything that costs registers spills and loses more than it saves:
-// all off 109.8 ms (125 registers, no spills) | SKIPLAST+FASTNAN+CONTRACT 131.4 (128 regs, 72 B spilled) |
-// SKIPLAST+CONTRACT 121.1 | FASTNAN+CONTRACT 133.1 | SKIPLAST+FASTNAN 129.7.
-#ifndef GCMF_OPT_SKIPLAST
-#define GCMF_OPT_SKIPLAST 0  // the last step of a block does not publish its result in shared memory
-#endif
-#ifndef GCMF_OPT_POLLWAIT
-#define GCMF_OPT_POLLWAIT 0  // neighbour waits poll mbarrier.test_wait instead of the parking try_wait
-#endif
-#ifndef GCMF_OPT_FASTNAN
-#define GCMF_OPT_FASTNAN 0   // FLUX: warp vote skips nan_to_num when every produced value is finite
-#endif
-#ifndef GCMF_OPT_BARPF
-#define GCMF_OPT_BARPF 0     // L2 prefetch of the next level's bar rows: 1 = one bulk prefetch per core row, 2 = per thread
-#endif
-#ifndef GCMF_OPT_EDGEREFILL
-// FLUX: who re-arms the landing tiles for the next level.  0: whichever warp drains them last (any of the 16, so the
-// ~300 instructions of address arithmetic and bulk-copy issue land on the critical path of a random inner warp, and
-// through the neighbour barriers on everybody's); 1: always warp 0, an edge warp that owns halo rows only and does
-// 6 of the inner warps' 16 row-steps per level -- it polls the drain counter between its steps.  NOT YET MEASURED
-// (written after the round-1 GPU budget was spent); parity-test on the GPU before switching it on.
-#define GCMF_OPT_EDGEREFILL 0
-#endif
-#ifndef GCMF_OPT_ROWPTR
-// 64-bit address arithmetic of load_bar / store: one full "level * bstride + first_row * pitch + column" per array
-// and level, then + q * pitch with the unrolled q, instead of a full 64-bit multiply-add per row and array (the
-// two phases are ~270 of the ~1730 instructions a warp spends per level, mostly IMAD).  NOT YET MEASURED.
-#define GCMF_OPT_ROWPTR 0
-#endif
-#ifndef GCMF_OPT_STATICMASK
-// REGULAR5: "has a wet mask" is a run-time flag that the step loop tests per point, which splits the unrolled row
-// loop into ~40 small basic blocks; with the switch on the loop is instantiated twice (masked / unmasked) and the
-// flag picks one per step.  NOT YET MEASURED.
-#define GCMF_OPT_STATICMASK 0
-#endif
-#ifndef GCMF_OPT_SANSTATE
-// FLUX: keep the SANITIZED T_{i-1} / T_{i-2} in the per-thread registers, plus one NaN bit and one inf bit per
-// value, instead of the raw values.  The sanitized value is what the Laplacian differences and what is published,
-// so (a) the thread's own rows no longer have to be read back from the work tile (4 of the 19 LDS.128 of a step,
-// and the 16 registers that held them: the kernel sits at the register cap, see above), and (b) nan_to_num runs
-// only for rows that produced a NaN / inf (one exponent test per value otherwise).  The raw value that the
-// point-wise terms "-x" and "- T_{i-2}" need is rebuilt from the bits (NaN, or inf with the sign of the sanitized
-// value), so results are bit-identical (NaN payloads aside).  NOT YET MEASURED; verified in the host emulator only.
-#define GCMF_OPT_SANSTATE 0
-#endif
-#ifndef GCMF_OPT_ROWNAN
-// FLUX: publish a row's new values as they are unless one of them is NaN / inf (one test on the exponent bits per
-// value and a branch per row) instead of running the 9-instruction branch-free nan_to_num on every value -- the
-// sanitizer is a third of the step loop's instructions.  Same results by construction.  NOT YET MEASURED.
-#define GCMF_OPT_ROWNAN 0
+// Compile-time knobs of the fused kernels.  Every one was A/B-measured on a B200 with tests/tools/build_variant.py +
+// variant_bench.py (cfg3 shape, 62 x 2400 x 3600 fp64, 44 steps, ms per filter call; profiles/variants_r02.md).  What the
+// round-2 A/B kept is unconditional code now: the landing tiles are re-armed by warp 0 (an edge warp with a third of
+// the inner warps' work: -4.4 %), the periodic index arithmetic of the loaders wraps once instead of dividing (-2.8 %),
+// FLUX hoists the 64-bit address arithmetic of load_bar / store, REGULAR5 resolves the mask flag per step (-2 %).
+// What lost is gone: sanitized state in registers (SANSTATE: +60 %, spills), per-row NaN branches (ROWNAN: +13 %), a
+// land-select publish with a running finiteness check instead of nan_to_num (FASTSAN: +7 % with tensor maps, +113 %
+// without; 24-42 bytes of spills), skipping the last publish, the warp-vote nan_to_num shortcut, bar L2 prefetch,
+// polling waits, a suspend-time hint on the parking waits (2 us / 20 us: +-0.1 %), contracting bar += p*T.
+// The FLUX kernel sits at the 128-register cap of a 512-thread CTA: anything that costs registers spills.
+#ifndef GCMF_OPT_TMAP
+// Interior tiles (no periodic wrap, no fold row) are staged by ONE cp.async.bulk.tensor (SASS UTMALDG) per array from a
+// cuTensorMapEncodeTiled descriptor instead of one cp.async.bulk per tile row issued by 32 lanes.
+#define GCMF_OPT_TMAP 1
 #endif
 
 // XS: how the tile row is split over threads.  1: one 16-byte vector per thread and row (512 threads, used by
@@ -136,46 +98,28 @@ template <typename T> struct FusedParams {
     int32_t levels_per_cta;
 };
 
+// Tensor-map descriptors (CUtensorMap, 128 opaque bytes, encoded on the host with cuTensorMapEncodeTiled) of the
+// arrays a launch stages through the TMA engine: boxes of one whole tile (TW x TH x 1 level).  A second
+// __grid_constant__ kernel parameter: cp.async.bulk.tensor takes the descriptor's address in parameter space.
+enum : int { TMAP_STATE = 1, TMAP_COEF = 2 };
+struct FusedMaps {
+    TmaDesc t1, t2;    // (nx, ny, nb) views of t1_in / t2_in
+    TmaDesc coef[3];   // (nx, ny) views of ce, cn, ra (FLUX)
+    int32_t use;       // TMAP_STATE | TMAP_COEF: which descriptors are valid (0: row-wise bulk copies everywhere)
+};
+
 template <typename T, int XS> struct FusedThread {  // per-thread registers that live across phases
     T t1[FusedGeom<T, XS>::R][FusedGeom<T, XS>::VX];   // raw T_{i-1} of the own points
     T t2[FusedGeom<T, XS>::R][FusedGeom<T, XS>::VX];   // raw T_{i-2}
     T acc[FusedGeom<T, XS>::R][FusedGeom<T, XS>::VX];  // running bar (owned points)
     uint32_t mbits;                             // REG5: wet bit of own point (q*VX+v)
     uint64_t wfbits;                            // REG5: wet_fac (0..4) of own point, 4 bits each
-    uint32_t nanbits, infbits;                  // SANSTATE: bit (16*a + q*VX+v): raw value of array a (0: t1, 1: t2) was NaN / inf
 };
 
-// SANSTATE: the raw value that nan_to_num turned into s
-template <typename T> GCMF_HD T raw_of(T s, bool was_nan, bool was_inf) {
-    if (was_nan) return (T)NAN;
-    if (was_inf) return s > T(0) ? (T)INFINITY : -(T)INFINITY;
-    return s;
-}
-
-// true if the predicate holds on any (converged) lane of the warp; the host emulator runs one thread at a time
-GCMF_HD bool warp_any(bool p) {
-#ifdef __CUDA_ARCH__
-    return __any_sync(__activemask(), p) != 0;
-#else
-    return p;
-#endif
-}
-
-#ifndef GCMF_OPT_WRAPONCE
-// Periodic index arithmetic of the tile loaders without the integer division: a fused plan's grid is at least one
-// tile wide and high, so every index handed to wrap_index lies in (-n, 2n) and one conditional add / subtract is
-// the modulo.  The `%` costs ~35 instructions each on the path of the warp that re-arms the landing tiles (four to
-// six of them per lane and level) and per gathered element next to a tripolar fold.  NOT YET MEASURED.
-#define GCMF_OPT_WRAPONCE 0
-#endif
-GCMF_HD int wrap_index(int v, int n) {
-#if GCMF_OPT_WRAPONCE
-    return v < 0 ? v + n : (v >= n ? v - n : v);
-#else
-    v %= n;
-    return v < 0 ? v + n : v;
-#endif
-}
+// Periodic index arithmetic of the tile loaders: a fused plan's grid is at least one tile wide and high, so every
+// index handed to wrap_index lies in (-n, 2n) and one conditional add / subtract is the modulo (a `%` costs ~35
+// instructions, four to six of them per lane and level on the path of the warp that re-arms the landing tiles).
+GCMF_HD int wrap_index(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
 
 // ---- bulk async copy global -> shared, completing on an mbarrier (device) / memcpy (host emulator) ----
 #ifdef __CUDACC__
@@ -189,6 +133,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* mb, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* mb) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mb)) : "memory");
 }
+// parking wait: the hardware suspends the warp until the phase completes or a time limit expires
 __device__ __forceinline__ void mbar_wait(uint64_t* mb, unsigned parity) {
     asm volatile(
         "{\n"
@@ -198,18 +143,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, unsigned parity) {
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(mb)), "r"(parity) : "memory");
-}
-// non-blocking variant: polls instead of letting the hardware park the warp (A/B switch GCMF_OPT_POLLWAIT)
-__device__ __forceinline__ void mbar_poll(uint64_t* mb, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "POLL_%=:\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra PDONE_%=;\n"
-        "bra POLL_%=;\n"
-        "PDONE_%=:\n"
         "}\n" ::"r"(smem_u32(mb)), "r"(parity) : "memory");
 }
 // ---- drain counter of the landing tiles (acquire-release at CTA scope) ----
@@ -225,6 +158,19 @@ __device__ __forceinline__ uint32_t ld_acquire_cta_u32(const uint32_t* p) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// one whole tile (box TW x TH [x 1 level]) through a tensor map: SASS UTMALDG
+__device__ __forceinline__ void tma_load_tile_3d(void* dst_smem, const TmaDesc* map, int x, int y, int z, uint64_t* mb) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+            "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(mb))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_tile_2d(void* dst_smem, const TmaDesc* map, int x, int y, uint64_t* mb) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(mb))
+        : "memory");
+}
 #endif
 
 GCMF_HD void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* mb) {
@@ -248,25 +194,38 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
     using G = FusedGeom<T, XS>;
     using Thread = FusedThread<T, XS>;
     const FusedParams<T>& P;
+    const FusedMaps* M;  // tensor maps of this launch (device: address in parameter space); nullptr in the host emulator
     int gy0, gx0;      // global coordinates of tile element (0,0) (may be negative: wraps)
     int cy0, cx0;      // global coordinates of the first core element
     T* smem;
     bool masked;       // REG5 with a wet mask (nan_to_num + mask), else raw values (NaNs spread)
+    bool interior;     // the whole tile (halo included) lies inside a periodic / tripolar grid: no wrap, no fold row
     static GCMF_HD constexpr bool is_first() { return (EDGE & 1) != 0; }
     static GCMF_HD constexpr bool is_last() { return (EDGE & 2) != 0; }
 
-    GCMF_HD FusedTile(const FusedParams<T>& P_, int tile, T* smem_) : P(P_), smem(smem_) {
+    GCMF_HD FusedTile(const FusedParams<T>& P_, int tile, T* smem_, const FusedMaps* M_ = nullptr)
+        : P(P_), M(M_), smem(smem_) {
         const int cx = tile % P.ncx, cy = tile / P.ncx;
         cy0 = cy * G::CH;
         cx0 = cx * G::CW;
         gy0 = cy0 - G::H;
         gx0 = cx0 - G::H;
         masked = (P.g.flags & FL_MASK) != 0;
+        interior = (P.g.flags & FL_WRAP_Y) && gx0 >= 0 && gx0 + G::TW <= P.g.nx && gy0 >= 0 && gy0 + G::TH <= P.g.ny;
     }
     GCMF_HD T* tileX() const { return smem; }
     GCMF_HD T* tileY() const { return smem + (size_t)G::PLANE; }
     GCMF_HD T* tileS(int which) const { return smem + (size_t)(2 + which) * G::PLANE; }
     GCMF_HD T* tileC(int which) const { return smem + (size_t)(4 + which) * G::PLANE; }
+    // does this tile take the tensor-map path for its state / coefficient tiles?
+    GCMF_HD bool tmap(int what) const {
+#if defined(__CUDA_ARCH__) && GCMF_OPT_TMAP
+        return interior && (M->use & what) != 0;
+#else
+        (void)what;
+        return false;
+#endif
+    }
 
     // value published to the neighbours: what the reference's Laplacian differences
     GCMF_HD T sanitize(T x, bool wet) const { return sanitize(x, wet, masked); }
@@ -300,12 +259,10 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
     // bytes of row r that arrive through bulk copies (the mbarrier's expected transaction count)
     GCMF_HD unsigned row_tx_bytes(int r) const { return virtual_row(r) ? 0u : (unsigned)(G::TW * sizeof(T)); }
 
-    // Stage tile row r of a (2-D slice of a) global array: <= 2 bulk copies (split at the x wrap), or a
-    // reversed gather for a virtual row.  dj / di: index shift applied to the image cell (coefficient faces).
-    GCMF_HD void copy_row(T* dst_tile, const T* src_slice, int64_t pitch, int r, uint64_t* mb, int dj = 0,
-                          int di = 0) const {
-        (void)dj; (void)di;
-        if (virtual_row(r)) return;  // gathered cooperatively by gather_virtual()
+    // Stage tile row r of a (2-D slice of a) global array: <= 2 bulk copies (split at the x wrap); the virtual rows
+    // of a tile next to the fold are gathered by gather_virtual().
+    GCMF_HD void copy_row(T* dst_tile, const T* src_slice, int64_t pitch, int r, uint64_t* mb) const {
+        if (virtual_row(r)) return;
         const int gy = source_row(r);
         const int gx = wrap_index(gx0, P.g.nx);
         const T* row = src_slice + (int64_t)gy * pitch;
@@ -314,6 +271,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         if (n1 < G::TW) bulk_copy_g2s(dst_tile + r * G::TW + n1, row, (unsigned)((G::TW - n1) * sizeof(T)), mb);
     }
     // Virtual rows of one tile, gathered by the TH issuing lanes together (lane strides over the columns).
+    // dj / di: index shift applied to the image cell (coefficient faces).
     GCMF_HD void gather_virtual(int lane, T* dst_tile, const T* src_slice, int64_t pitch, int dj = 0, int di = 0) const {
         if (!fold()) return;
         int r0 = P.g.ny - gy0;  // first virtual tile row
@@ -323,11 +281,23 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
             for (int c = lane; c < G::TW; c += G::TH) dst_tile[r * G::TW + c] = row[wrap_index(image_col(c) + di, P.g.nx)];
         }
     }
-    // phase: thread r < TH stages the coefficient rows (FLUX).  Returns the bulk bytes it issued.
+    // phase: lane r < TH stages the coefficient rows (FLUX) and arrives on the barrier with the bytes it expects;
+    // an interior tile is three tensor copies issued by lane 0 instead.
     GCMF_HD unsigned coef_tx_bytes(int r) const {
         return virtual_row(r) ? 0u : (below_cut(r) ? 2u : 3u) * (unsigned)(G::TW * sizeof(T));
     }
-    GCMF_HD void issue_coef_row(int r, uint64_t* mb) const {
+    GCMF_HD void issue_coef(int r, uint64_t* mb) const {
+#if defined(__CUDA_ARCH__) && GCMF_OPT_TMAP
+        if (tmap(TMAP_COEF)) {
+            if (r == 0) {
+                mbar_expect_tx(mb, 3u * (unsigned)(G::PLANE * sizeof(T)));
+                for (int s = 0; s < 3; ++s) tma_load_tile_2d(tileC(s), &M->coef[s], gx0, gy0, mb);
+            } else {
+                mbar_arrive(mb);
+            }
+            return;
+        }
+#endif
         const T* ce = reinterpret_cast<const T*>(P.plane[0].p);
         const T* cn = reinterpret_cast<const T*>(P.plane[1].p);
         const T* ra = reinterpret_cast<const T*>(P.plane[2].p);
@@ -335,21 +305,39 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         gather_virtual(r, tileC(0), ce, P.plane[0].pitch, 0, -1);
         gather_virtual(r, tileC(1), cn, P.plane[1].pitch, -1, 0);
         gather_virtual(r, tileC(2), ra, P.plane[2].pitch);
-        copy_row(tileC(0), ce, P.plane[0].pitch, r, mb, 0, -1);
+        copy_row(tileC(0), ce, P.plane[0].pitch, r, mb);
         if (below_cut(r)) {  // no flux across the southern edge of row 0 (and nothing below it matters)
             for (int c = 0; c < G::TW; ++c) tileC(1)[r * G::TW + c] = T(0);
         } else {
-            copy_row(tileC(1), cn, P.plane[1].pitch, r, mb, -1, 0);
+            copy_row(tileC(1), cn, P.plane[1].pitch, r, mb);
         }
         copy_row(tileC(2), ra, P.plane[2].pitch, r, mb);
+#ifdef __CUDA_ARCH__
+        mbar_expect_tx(mb, coef_tx_bytes(r));  // generic writes (virtual / cut rows) precede this releasing arrive
+#endif
     }
-    // phase: thread r < TH issues row r of T1(level) -> X and T2(level) -> Y
+    // phase: lane r < TH issues row r of T1(level) -> X and T2(level) -> Y (interior tile: lane 0 issues two boxes)
     GCMF_HD unsigned state_tx_bytes(int r) const { return (is_first() ? 1u : 2u) * row_tx_bytes(r); }
-    GCMF_HD void issue_state_row(int r, int64_t level, uint64_t* mb) const {
+    GCMF_HD void issue_state(int r, int64_t level, uint64_t* mb) const {
+#if defined(__CUDA_ARCH__) && GCMF_OPT_TMAP
+        if (tmap(TMAP_STATE)) {
+            if (r == 0) {
+                mbar_expect_tx(mb, (is_first() ? 1u : 2u) * (unsigned)(G::PLANE * sizeof(T)));
+                tma_load_tile_3d(tileX(), &M->t1, gx0, gy0, (int)level, mb);
+                if (!is_first()) tma_load_tile_3d(tileY(), &M->t2, gx0, gy0, (int)level, mb);
+            } else {
+                mbar_arrive(mb);
+            }
+            return;
+        }
+#endif
         gather_virtual(r, tileX(), P.t1_in.p + level * P.t1_in.bstride, P.t1_in.pitch);
         if (!is_first()) gather_virtual(r, tileY(), P.t2_in.p + level * P.t2_in.bstride, P.t2_in.pitch);
         copy_row(tileX(), P.t1_in.p + level * P.t1_in.bstride, P.t1_in.pitch, r, mb);
         if (!is_first()) copy_row(tileY(), P.t2_in.p + level * P.t2_in.bstride, P.t2_in.pitch, r, mb);
+#ifdef __CUDA_ARCH__
+        mbar_expect_tx(mb, state_tx_bytes(r));
+#endif
     }
 
     GCMF_HD bool owns_cols(int tx) const {
@@ -398,56 +386,27 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         st.wfbits = wf;
     }
 
-    // `bar` is the one array of a block that is loaded synchronously (straight into the accumulator registers at
-    // the top of a level); these hints pull the next level's rows into L2 while the current level is computed, so
-    // that load is an L2 hit.  Prefetches have no architectural effect: results cannot depend on them.
-    GCMF_HD void prefetch_bar_row(int r, int64_t level) const {  // one bulk prefetch per owned tile row (lane r < TH)
-#ifdef __CUDA_ARCH__
-        if (is_first() || !owns_row(r)) return;
-        int w = P.g.nx - cx0;
-        if (w > G::CW) w = G::CW;  // core columns inside the grid: a multiple of the 16-byte vector
-        const T* row = P.bar.p + level * P.bar.bstride + (int64_t)(cy0 + r - G::H) * P.bar.pitch + cx0;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"((unsigned)(w * sizeof(T))) : "memory");
-#else
-        (void)r; (void)level;
-#endif
-    }
-    GCMF_HD void prefetch_bar_own(int tid, int64_t level) const {  // every thread hints the lines of its own points
-#ifdef __CUDA_ARCH__
-        const int tx = tid % G::NTX, ty = tid / G::NTX;
-        if (is_first() || !owns_cols(tx)) return;
-#pragma unroll
-        for (int q = 0; q < G::R; ++q) {
-            const int lr = ty * G::R + q;
-            if (!owns_row(lr)) continue;
-            const T* ptr = P.bar.p + level * P.bar.bstride + (int64_t)(cy0 + lr - G::H) * P.bar.pitch +
-                           (cx0 + tx * G::VX - G::H);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr) : "memory");
-        }
-#else
-        (void)tid; (void)level;
-#endif
-    }
+    // FLUX hoists the 64-bit address arithmetic of load_bar / store: one full "level * bstride + first_row * pitch +
+    // column" per array and level, then + q * pitch with the unrolled q (A/B: FLUX gains with the hoisting in place,
+    // the REGULAR5 kernel loses 3 % with it and keeps the per-row form).
+    static constexpr bool ROWPTR = KIND == FK_FLUX;
 
     // phase: bar of the owned points from HBM into registers
     GCMF_HD void load_bar(int tid, int64_t level, Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         const bool oc = owns_cols(tx);
-#if GCMF_OPT_ROWPTR
         const int64_t ob = level * P.bar.bstride + (int64_t)(cy0 + ty * G::R - G::H) * P.bar.pitch +
                            (cx0 + lc0 - G::H);  // element offset of the thread's first row
-#endif
 #pragma unroll
         for (int q = 0; q < G::R; ++q) {
             const int lr = ty * G::R + q;
             if (oc && owns_row(lr) && !is_first()) {
-#if GCMF_OPT_ROWPTR
-                Ld<T, G::VX>::go(P.bar.p + (ob + (int64_t)q * P.bar.pitch), st.acc[q]);
-#else
-                Ld<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)(cy0 + lr - G::H) * P.bar.pitch +
-                                     (cx0 + lc0 - G::H), st.acc[q]);
-#endif
+                if (ROWPTR)
+                    Ld<T, G::VX>::go(P.bar.p + (ob + (int64_t)q * P.bar.pitch), st.acc[q]);
+                else
+                    Ld<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)(cy0 + lr - G::H) * P.bar.pitch +
+                                         (cx0 + lc0 - G::H), st.acc[q]);
             } else {
 #pragma unroll
                 for (int v = 0; v < G::VX; ++v) st.acc[q][v] = T(0);
@@ -456,56 +415,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
     }
 
     // phase: lift the raw own points out of the landing tiles, publish the sanitized T1 in S0
-    static constexpr bool SANSTATE = GCMF_OPT_SANSTATE && KIND == FK_FLUX;
-    static constexpr uint32_t ROWMASK = (1u << G::VX) - 1u;
-    static_assert(G::R * G::VX <= 16, "SANSTATE keeps 16 flag bits per array");
-
-    // SANSTATE form of extract: registers and S0 receive nan_to_num(T1) (and nan_to_num(T2)), the flag bits remember
-    // what was NaN / inf
-    GCMF_HD void extract_ss(int tid, Thread& st) const {
-        const int tx = tid % G::NTX, ty = tid / G::NTX;
-        const int lc0 = tx * G::VX;
-        const T* X = tileX();
-        const T* Y = tileY();
-        T* S0 = tileS(0);
-        uint32_t nb = 0, ib = 0;
-#pragma unroll
-        for (int q = 0; q < G::R; ++q) {
-            const int off = (ty * G::R + q) * G::TW + lc0;
-            Ld<T, G::VX>::go(X + off, st.t1[q]);
-            if (!is_first()) {
-                Ld<T, G::VX>::go(Y + off, st.t2[q]);
-            } else {
-#pragma unroll
-                for (int v = 0; v < G::VX; ++v) st.t2[q][v] = T(0);
-            }
-            bool nf = false;
-#pragma unroll
-            for (int v = 0; v < G::VX; ++v) nf = nf || nonfinite(st.t1[q][v]) || nonfinite(st.t2[q][v]);
-            if (nf) {
-#pragma unroll
-                for (int v = 0; v < G::VX; ++v) {
-                    const int idx = q * G::VX + v;
-                    const T r1 = st.t1[q][v], r2 = st.t2[q][v];
-                    if (r1 != r1) nb |= 1u << idx;
-                    else if (nonfinite(r1)) ib |= 1u << idx;
-                    if (r2 != r2) nb |= 1u << (16 + idx);
-                    else if (nonfinite(r2)) ib |= 1u << (16 + idx);
-                    st.t1[q][v] = nan2num(r1);
-                    st.t2[q][v] = nan2num(r2);
-                }
-            }
-            St<T, G::VX>::go(S0 + off, st.t1[q]);
-        }
-        st.nanbits = nb;
-        st.infbits = ib;
-    }
-
     GCMF_HD void extract(int tid, Thread& st) const {
-        if (SANSTATE) {
-            extract_ss(tid, st);
-            return;
-        }
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         const T* X = tileX();
@@ -532,11 +442,10 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
     // X1 holds T_{i-1} (raw), X2 holds T_{i-2}; the new T_i is written over X2, so consecutive steps just swap
     // the roles of the two register arrays (no moves).  ALLROWS: the thread's R rows all lie in the region for
     // every s <= H (its rows are core rows), which removes every branch from the row loop.
-    // MSK: -1 = the run-time flag `masked`, 0 / 1 = known at compile time (GCMF_OPT_STATICMASK)
-    template <bool ALLROWS, int MSK = -1>
+    // MSK (REGULAR5): "has a wet mask", resolved per step instead of per point (straight-line row loop).
+    template <bool ALLROWS, bool MSK>
     GCMF_HD void step_rows(int tid, int s, const T* __restrict__ S, T* __restrict__ D, T (&X1)[G::R][G::VX],
                            T (&X2)[G::R][G::VX], Thread& st) const {
-        const bool msk = MSK < 0 ? masked : MSK != 0;
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         const int lr0 = ty * G::R;
@@ -547,12 +456,6 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         const T c = (T)P.c;
         const double pk = P.p[s - 1];
         const bool start = is_first() && s == 1;  // recurrence step 1: T_1 = A(x), bar = p0 x + p1 T_1
-        // Nobody reads what the block's last step would publish (the next level starts from the landing tiles).
-        const bool publish = !GCMF_OPT_SKIPLAST || s < P.k;
-        // FLUX, inner threads: publish after the row loop, and skip nan_to_num altogether when no lane of the warp
-        // produced a NaN / inf (sanitize is the identity on finite values, so the vote is only a shortcut).
-        constexpr bool DEFER = GCMF_OPT_FASTNAN && ALLROWS && KIND == FK_FLUX;
-        constexpr bool CONTRACT = GCMF_OPT_CONTRACT && KIND == FK_FLUX;  // as OpFlux in the one-step kernels
         T o[G::R][G::VX], os[G::VX], on[G::VX];
 #pragma unroll
         for (int q = 0; q < G::R; ++q) Ld<T, G::VX>::go(Sc + q * G::TW, o[q]);  // = sanitize(X1), published by this thread
@@ -607,7 +510,7 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                     const T o_s = q == 0 ? os[v] : o[q > 0 ? q - 1 : 0][v];
                     const int idx = q * G::VX + v;
                     T lap;
-                    if (msk) {  // kernels.py:178-186
+                    if (MSK) {  // kernels.py:178-186
                         const T wf = (T)(int)((st.wfbits >> (4 * idx)) & 0xfull);
                         const T r = (((-wf * o[q][v] + o_e) + o_w) + o_n) + o_s;
                         lap = ((st.mbits >> idx) & 1u) ? r : T(0);
@@ -621,176 +524,17 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
 #pragma unroll
             for (int v = 0; v < G::VX; ++v) {
                 const double b0 = start ? P.p0 * (double)X1[q][v] : (double)st.acc[q][v];
-                st.acc[q][v] = (T)bar_update<CONTRACT>(b0, pk, (double)t0[v]);  // filter.py:195 / 204
-                X2[q][v] = t0[v];                                               // T_i replaces T_{i-2}
+                st.acc[q][v] = (T)bar_update(b0, pk, (double)t0[v]);  // filter.py:195 / 204
+                X2[q][v] = t0[v];                                     // T_i replaces T_{i-2}
             }
-            if (GCMF_OPT_ROWNAN && KIND == FK_FLUX && !DEFER && publish) {
-                bool nf = false;
 #pragma unroll
-                for (int v = 0; v < G::VX; ++v) nf = nf || nonfinite(t0[v]);
-                if (nf) {
-#pragma unroll
-                    for (int v = 0; v < G::VX; ++v) pub[v] = nan2num(t0[v]);
-                    St<T, G::VX>::go(D + off0 + q * G::TW, pub);
-                } else {
-                    St<T, G::VX>::go(D + off0 + q * G::TW, t0);
-                }
-            } else if (!DEFER && publish) {
-#pragma unroll
-                for (int v = 0; v < G::VX; ++v) pub[v] = sanitize(t0[v], (st.mbits >> (q * G::VX + v)) & 1u, msk);
-                St<T, G::VX>::go(D + off0 + q * G::TW, pub);
-            }
-        }
-        if (DEFER && publish) {
-            bool nf = false;
-#pragma unroll
-            for (int q = 0; q < G::R; ++q)
-#pragma unroll
-                for (int v = 0; v < G::VX; ++v) nf = nf || nonfinite(X2[q][v]);
-            if (warp_any(nf)) {
-#pragma unroll
-                for (int q = 0; q < G::R; ++q) {
-                    T pub[G::VX];
-#pragma unroll
-                    for (int v = 0; v < G::VX; ++v) pub[v] = sanitize(X2[q][v], true);
-                    St<T, G::VX>::go(D + off0 + q * G::TW, pub);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < G::R; ++q) St<T, G::VX>::go(D + off0 + q * G::TW, X2[q]);
-            }
+            for (int v = 0; v < G::VX; ++v) pub[v] = sanitize(t0[v], (st.mbits >> (q * G::VX + v)) & 1u, MSK);
+            St<T, G::VX>::go(D + off0 + q * G::TW, pub);
         }
     }
 
-    // SANSTATE form of step_rows (FLUX only): X1 / X2 hold sanitized values, a1 = 0 when X1 is st.t1 (else 1) selects
-    // their flag bits.  The thread's own rows come from X1, only the rows above / below and the W / E columns from S.
-    // Three forms, one per warp and step:
-    //   MODE 0  no value of the warp's threads is flagged: branch-free row loop without any sanitizer arithmetic;
-    //   MODE 1  NaN flags only (land points of a NaN-masked field: the common case): the same loop, and a flagged
-    //           point's new value is forced to NaN afterwards -- which is what -NaN - c*Lap and 2A - NaN give;
-    //   MODE 2  an inf flag somewhere: the raw values of the point-wise terms are rebuilt from the bits (selects).
-    // In every form the new values are examined after the loop and only a fresh NaN / inf among them triggers
-    // nan_to_num and the flag update of that value; the rows are published last.
-    template <bool ALLROWS, int MODE>
-    GCMF_HD void step_rows_ss(int tid, int s, const T* __restrict__ S, T* __restrict__ D, T (&X1)[G::R][G::VX],
-                              T (&X2)[G::R][G::VX], int a1, Thread& st) const {
-        const int tx = tid % G::NTX, ty = tid / G::NTX;
-        const int lc0 = tx * G::VX;
-        const int lr0 = ty * G::R;
-        const int off0 = lr0 * G::TW + lc0;
-        const T* Sc = S + off0;
-        const T* Sw = Sc - (lc0 > 0 ? 1 : 0);
-        const T* Se = Sc + (lc0 + G::VX < G::TW ? G::VX : G::VX - 1);
-        const T c = (T)P.c;
-        const double pk = P.p[s - 1];
-        const bool start = is_first() && s == 1;
-        const bool publish = !GCMF_OPT_SKIPLAST || s < P.k;
-        constexpr bool CONTRACT = GCMF_OPT_CONTRACT != 0;
-        const int f1 = a1 * 16, f2 = (a1 ^ 1) * 16;
-        // MODE 1: points whose T_{i-1} or T_{i-2} is NaN; their T_i is NaN
-        const uint32_t force = MODE == 1 ? ((st.nanbits >> f1) | (st.nanbits >> f2)) & 0xffffu : 0u;
-        uint32_t region = 0;  // bit (q*VX+v) set for the rows this step computes
-        T os[G::VX], on[G::VX];
-        if (ALLROWS || lr0 > 0) Ld<T, G::VX>::go(Sc - G::TW, os);
-        if (ALLROWS || lr0 + G::R < G::TH) Ld<T, G::VX>::go(Sc + G::R * G::TW, on);
-        T cn_prev[G::VX];
-        bool have_prev = false;
-#pragma unroll
-        for (int q = 0; q < G::R; ++q) {
-            const int lr = lr0 + q;
-            if (!ALLROWS && (lr < s || lr >= G::TH - s)) {
-                have_prev = false;
-                continue;
-            }
-            region |= ROWMASK << (q * G::VX);
-            const T ow = Sw[q * G::TW];
-            const T oe = Se[q * G::TW];
-            const T* CE = tileC(0) + off0 + q * G::TW;
-            const T* CN = tileC(1) + off0 + q * G::TW;
-            const T* RA = tileC(2) + off0 + q * G::TW;
-            T ce[G::VX], cn[G::VX], cs[G::VX], ra[G::VX];
-            Ld<T, G::VX>::go(CE, ce);
-            const T cew = *(CE - (lc0 > 0 ? 1 : 0));
-            Ld<T, G::VX>::go(CN, cn);
-            if ((ALLROWS && q > 0) || have_prev) {
-#pragma unroll
-                for (int v = 0; v < G::VX; ++v) cs[v] = cn_prev[v];
-            } else {
-                Ld<T, G::VX>::go(CN - G::TW, cs);
-            }
-            Ld<T, G::VX>::go(RA, ra);
-#pragma unroll
-            for (int v = 0; v < G::VX; ++v) {
-                const int idx = q * G::VX + v;
-                const T o_e = v == G::VX - 1 ? oe : X1[q][v + 1 < G::VX ? v + 1 : v];
-                const T o_w = v == 0 ? ow : X1[q][v > 0 ? v - 1 : 0];
-                const T o_n = q == G::R - 1 ? on[v] : X1[q + 1 < G::R ? q + 1 : q][v];
-                const T o_s = q == 0 ? os[v] : X1[q > 0 ? q - 1 : 0][v];
-                const T lap = flux_lap<T>(X1[q][v], o_w, o_e, o_n, o_s, ce[v], v == 0 ? cew : ce[v > 0 ? v - 1 : 0],
-                                          cn[v], cs[v], ra[v]);
-                T x = X1[q][v], t2 = X2[q][v];
-                if (MODE == 2) {  // rebuild the raw values of the point-wise terms
-                    x = raw_of<T>(x, (st.nanbits >> (f1 + idx)) & 1u, (st.infbits >> (f1 + idx)) & 1u);
-                    t2 = raw_of<T>(t2, (st.nanbits >> (f2 + idx)) & 1u, (st.infbits >> (f2 + idx)) & 1u);
-                }
-                const T a = shifted_flux<T>(x, c, lap);                  // filter.py:171
-                T t0 = start ? a : cheb_next<T>(a, t2);                  // filter.py:192-194 / 197-203
-                if (MODE == 1 && ((force >> idx) & 1u)) t0 = (T)NAN;
-                const double b0 = start ? P.p0 * (double)x : (double)st.acc[q][v];
-                st.acc[q][v] = (T)bar_update<CONTRACT>(b0, pk, (double)t0);  // filter.py:195 / 204
-                X2[q][v] = (MODE == 1 && ((force >> idx) & 1u)) ? T(0) : t0;  // T_i replaces T_{i-2} (NaN -> 0)
-                cn_prev[v] = cn[v];
-            }
-            have_prev = true;
-        }
-        if (MODE == 1)  // the forced points are the NaNs of T_i so far; no inf bits exist in this mode
-            st.nanbits = (st.nanbits & ~(region << f2)) | ((force & region) << f2);
-        // a fresh NaN / inf among the new values (MODE 2: any value at all) gets its flags and nan_to_num
-        bool nf = MODE == 2;
-        if (MODE != 2) {
-#pragma unroll
-            for (int q = 0; q < G::R; ++q)
-#pragma unroll
-                for (int v = 0; v < G::VX; ++v)
-                    if ((region >> (q * G::VX + v)) & 1u) nf = nf || nonfinite(X2[q][v]);
-        }
-        if (nf) {
-#pragma unroll
-            for (int q = 0; q < G::R; ++q) {
-#pragma unroll
-                for (int v = 0; v < G::VX; ++v) {
-                    const int idx = q * G::VX + v;
-                    if (!((region >> idx) & 1u) || ((force >> idx) & 1u)) continue;
-                    const uint32_t bit = 1u << (f2 + idx);
-                    const T t0 = X2[q][v];
-                    const bool isn = t0 != t0;
-                    const bool isi = !isn && nonfinite(t0);
-                    st.nanbits = isn ? (st.nanbits | bit) : (st.nanbits & ~bit);
-                    st.infbits = isi ? (st.infbits | bit) : (st.infbits & ~bit);
-                    X2[q][v] = nan2num(t0);
-                }
-            }
-        }
-        if (publish) {
-#pragma unroll
-            for (int q = 0; q < G::R; ++q)
-                if ((region >> (q * G::VX)) & 1u) St<T, G::VX>::go(D + off0 + q * G::TW, X2[q]);
-        }
-    }
-
-    template <int MODE> GCMF_HD void step_ss(int tid, int s, bool inner, Thread& st) const {
-        const T* Ssrc = (s & 1) ? tileS(0) : tileS(1);
-        T* Sdst = (s & 1) ? tileS(1) : tileS(0);
-        if (s & 1) {
-            if (inner) step_rows_ss<true, MODE>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
-            else step_rows_ss<false, MODE>(tid, s, Ssrc, Sdst, st.t1, st.t2, 0, st);
-        } else {
-            if (inner) step_rows_ss<true, MODE>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
-            else step_rows_ss<false, MODE>(tid, s, Ssrc, Sdst, st.t2, st.t1, 1, st);
-        }
-    }
-
-    template <int MSK> GCMF_HD void step_static(int tid, int s, bool inner, Thread& st) const {
+    template <bool MSK> GCMF_HD void step_msk(int tid, int s, bool inner, Thread& st) const {
+        // odd steps read T_{i-1} from st.t1 and overwrite st.t2; even steps the other way round
         if (s & 1) {
             if (inner) step_rows<true, MSK>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
             else step_rows<false, MSK>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
@@ -800,33 +544,13 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         }
     }
 
-    // odd steps read T_{i-1} from st.t1 and overwrite st.t2; even steps the other way round
     GCMF_HD void step(int tid, int s, Thread& st) const {
         const int tx = tid % G::NTX, ty = tid / G::NTX;
         const int lc0 = tx * G::VX;
         if (lc0 + G::VX <= s || lc0 >= G::TW - s) return;  // column group outside the region
         const bool inner = ty * G::R >= G::H && (ty + 1) * G::R <= G::TH - G::H;  // rows inside for every s <= H
-        if (SANSTATE) {
-            // one code path per warp: as general as its most demanding thread needs
-            const bool any_inf = warp_any(st.infbits != 0u);
-            const bool any_nan = warp_any(st.nanbits != 0u);
-            if (any_inf) step_ss<2>(tid, s, inner, st);
-            else if (any_nan) step_ss<1>(tid, s, inner, st);
-            else step_ss<0>(tid, s, inner, st);
-            return;
-        }
-        if (GCMF_OPT_STATICMASK && KIND == FK_REG5) {
-            if (masked) step_static<1>(tid, s, inner, st);
-            else step_static<0>(tid, s, inner, st);
-            return;
-        }
-        if (s & 1) {
-            if (inner) step_rows<true>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
-            else step_rows<false>(tid, s, tileS(0), tileS(1), st.t1, st.t2, st);
-        } else {
-            if (inner) step_rows<true>(tid, s, tileS(1), tileS(0), st.t2, st.t1, st);
-            else step_rows<false>(tid, s, tileS(1), tileS(0), st.t2, st.t1, st);
-        }
+        if (KIND == FK_REG5 && masked) step_msk<true>(tid, s, inner, st);
+        else step_msk<false>(tid, s, inner, st);
     }
 
     // phase: write the owned core points of T_{i+k-1}, T_{i+k-2} and bar back to HBM (from registers)
@@ -835,19 +559,11 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
         if (!owns_cols(tx)) return;
         const int lc0 = tx * G::VX;
         const int gx = cx0 + lc0 - G::H;
-#if GCMF_OPT_ROWPTR
-        const int gyf = cy0 + ty * G::R - G::H;  // element offsets of the thread's first row in the output arrays
+        const int gyf = cy0 + ty * G::R - G::H;  // first row of the thread
+        // element offsets of the thread's first row in the output arrays (ROWPTR form)
         const int64_t ob0 = level * P.bar.bstride + (int64_t)gyf * P.bar.pitch + gx;
         const int64_t o10 = is_last() ? 0 : level * P.t1_out.bstride + (int64_t)gyf * P.t1_out.pitch + gx;
         const int64_t o20 = is_last() ? 0 : level * P.t2_out.bstride + (int64_t)gyf * P.t2_out.pitch + gx;
-#define GCMF_BAR_ROW(q_, gy_) (P.bar.p + (ob0 + (int64_t)(q_) * P.bar.pitch))
-#define GCMF_T1_ROW(q_, gy_) (P.t1_out.p + (o10 + (int64_t)(q_) * P.t1_out.pitch))
-#define GCMF_T2_ROW(q_, gy_) (P.t2_out.p + (o20 + (int64_t)(q_) * P.t2_out.pitch))
-#else
-#define GCMF_BAR_ROW(q_, gy_) (P.bar.p + level * P.bar.bstride + (int64_t)(gy_) * P.bar.pitch + gx)
-#define GCMF_T1_ROW(q_, gy_) (P.t1_out.p + level * P.t1_out.bstride + (int64_t)(gy_) * P.t1_out.pitch + gx)
-#define GCMF_T2_ROW(q_, gy_) (P.t2_out.p + level * P.t2_out.bstride + (int64_t)(gy_) * P.t2_out.pitch + gx)
-#endif
 #pragma unroll
         for (int q = 0; q < G::R; ++q) {
             const int lr = ty * G::R + q;
@@ -864,61 +580,33 @@ template <typename T, int KIND, int EDGE> struct FusedTile {
                     for (int v = 0; v < G::VX; ++v) outv[v] = outv[v] / ar[v];
                 }
             } else {
-                // after an odd number of steps the newest T sits in st.t2 (see step())
-                if (SANSTATE) {  // the arrays in HBM hold raw values
-                    T n1[G::VX], n2[G::VX];
-                    const int fa = (P.k & 1) ? 16 : 0, fb = (P.k & 1) ? 0 : 16;
+                // after an odd number of steps the newest T sits in st.t2 (see step_msk()).  Value selects: a select
+                // between the two register ARRAYS can push the whole per-thread state into local memory (ptxas -v
+                // once showed a 128-byte stack frame for fused_kernel<double, REG5>).
+                T n1[G::VX], n2[G::VX];
 #pragma unroll
-                    for (int v = 0; v < G::VX; ++v) {
-                        const int idx = q * G::VX + v;
-                        n1[v] = raw_of<T>((P.k & 1) ? st.t2[q][v] : st.t1[q][v], (st.nanbits >> (fa + idx)) & 1u,
-                                          (st.infbits >> (fa + idx)) & 1u);
-                        n2[v] = raw_of<T>((P.k & 1) ? st.t1[q][v] : st.t2[q][v], (st.nanbits >> (fb + idx)) & 1u,
-                                          (st.infbits >> (fb + idx)) & 1u);
-                    }
-                    St<T, G::VX>::go(GCMF_T1_ROW(q, gy), n1);
-                    St<T, G::VX>::go(GCMF_T2_ROW(q, gy), n2);
-                } else {
-#if GCMF_OPT_ROWPTR
-                T n1[G::VX], n2[G::VX];  // value selects: a select between the two register arrays themselves can
-#pragma unroll                           // push the whole per-thread state into local memory
                 for (int v = 0; v < G::VX; ++v) {
                     n1[v] = (P.k & 1) ? st.t2[q][v] : st.t1[q][v];
                     n2[v] = (P.k & 1) ? st.t1[q][v] : st.t2[q][v];
                 }
-                St<T, G::VX>::go(GCMF_T1_ROW(q, gy), n1);
-                St<T, G::VX>::go(GCMF_T2_ROW(q, gy), n2);
-#else
-                if (KIND == FK_REG5) {
-                    // value selects: ptxas -v showed a 128-byte stack frame for fused_kernel<double, REG5> -- the
-                    // select between the two register arrays below had pushed t1 / t2 / acc into local memory
-                    T n1[G::VX], n2[G::VX];
-#pragma unroll
-                    for (int v = 0; v < G::VX; ++v) {
-                        n1[v] = (P.k & 1) ? st.t2[q][v] : st.t1[q][v];
-                        n2[v] = (P.k & 1) ? st.t1[q][v] : st.t2[q][v];
-                    }
-                    St<T, G::VX>::go(GCMF_T1_ROW(q, gy), n1);
-                    St<T, G::VX>::go(GCMF_T2_ROW(q, gy), n2);
+                if (ROWPTR) {
+                    St<T, G::VX>::go(P.t1_out.p + (o10 + (int64_t)q * P.t1_out.pitch), n1);
+                    St<T, G::VX>::go(P.t2_out.p + (o20 + (int64_t)q * P.t2_out.pitch), n2);
                 } else {
-                St<T, G::VX>::go(GCMF_T1_ROW(q, gy), (P.k & 1) ? st.t2[q] : st.t1[q]);
-                St<T, G::VX>::go(GCMF_T2_ROW(q, gy), (P.k & 1) ? st.t1[q] : st.t2[q]);
-                }
-#endif
+                    St<T, G::VX>::go(P.t1_out.p + level * P.t1_out.bstride + (int64_t)gy * P.t1_out.pitch + gx, n1);
+                    St<T, G::VX>::go(P.t2_out.p + level * P.t2_out.bstride + (int64_t)gy * P.t2_out.pitch + gx, n2);
                 }
             }
-            St<T, G::VX>::go(GCMF_BAR_ROW(q, gy), outv);
+            if (ROWPTR) St<T, G::VX>::go(P.bar.p + (ob0 + (int64_t)q * P.bar.pitch), outv);
+            else St<T, G::VX>::go(P.bar.p + level * P.bar.bstride + (int64_t)gy * P.bar.pitch + gx, outv);
         }
     }
-#undef GCMF_BAR_ROW
-#undef GCMF_T1_ROW
-#undef GCMF_T2_ROW
 };
 
 #ifdef __CUDACC__
 template <typename T, int KIND, int EDGE>
 __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREADS, 1)
-    fused_kernel(const __grid_constant__ FusedParams<T> P) {
+    fused_kernel(const __grid_constant__ FusedParams<T> P, const __grid_constant__ FusedMaps M) {
     using G = FusedGeom<T, FusedSplit<KIND>::value>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
@@ -930,7 +618,7 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
     const int64_t l0 = (int64_t)grp * P.levels_per_cta;
     const int64_t l1 = l0 + P.levels_per_cta < P.nb ? l0 + P.levels_per_cta : P.nb;
     if (l0 >= l1) return;
-    FusedTile<T, KIND, EDGE> tl(P, tile, smem);
+    FusedTile<T, KIND, EDGE> tl(P, tile, smem, &M);
     typename FusedTile<T, KIND, EDGE>::Thread st;
     if (tid == 0) {
         mbar_init(&mb[0], G::TH);
@@ -949,12 +637,8 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
     static_assert(G::TH <= 32 && G::NTHREADS <= 1024, "one refill lane per tile row");
     __syncthreads();
     if (tid < G::TH) {
-        if (KIND == FK_FLUX) {
-            tl.issue_coef_row(tid, &mb[0]);  // generic writes (virtual / cut rows) precede the releasing arrive
-            mbar_expect_tx(&mb[0], tl.coef_tx_bytes(tid));
-        }
-        tl.issue_state_row(tid, l0, &mb[1]);
-        mbar_expect_tx(&mb[1], tl.state_tx_bytes(tid));
+        if (KIND == FK_FLUX) tl.issue_coef(tid, &mb[0]);
+        tl.issue_state(tid, l0, &mb[1]);
     }
     tl.load_mask(tid, st);
     // FLUX steps are long enough for neighbour-only synchronisation to pay; the light REGULAR5 steps keep
@@ -964,17 +648,13 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
     int it = 0;
     for (int64_t l = l0; l < l1; ++l, ++it) {
         tl.load_bar(tid, l, st);
-        if (KIND == FK_FLUX && it == 0) mbar_wait(&mb[0], 0);
         mbar_wait(&mb[1], (unsigned)(it & 1));
         tl.extract(tid, st);
         __syncthreads();  // S0 complete; landing tiles consumed
         if (l + 1 < l1 && tid < G::TH) {  // next level's tiles fly during the k steps
             fence_proxy_async();
-            tl.issue_state_row(tid, l + 1, &mb[1]);
-            mbar_expect_tx(&mb[1], tl.state_tx_bytes(tid));
-            if (GCMF_OPT_BARPF == 1) tl.prefetch_bar_row(tid, l + 1);
+            tl.issue_state(tid, l + 1, &mb[1]);
         }
-        if (GCMF_OPT_BARPF == 2 && l + 1 < l1) tl.prefetch_bar_own(tid, l + 1);
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {
             tl.step(tid, s, st);
@@ -991,7 +671,7 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
     // hop, which spreads shared-memory and fp64 work in time instead of convoying at a barrier.
     // Progress is signalled through mbarriers rather than polled flags: a warp that has completed phase g
     // arrives (release) on barrier [g & 1] of each neighbour; a warp about to start phase g+1 waits (acquire, the
-    // hardware parks it: no polling instructions) on its own barrier [g & 1], whose expected arrival count is its
+    // hardware parks it) on its own barrier [g & 1], whose expected arrival count is its
     // number of neighbours.  Two barriers per warp suffice because a neighbour can complete phase g+2 only after
     // this warp has completed g+1, i.e. after it has consumed phase g of the same barrier.
     uint64_t* nbar = mb + 2;                                          // [NWARPS][2]
@@ -1007,11 +687,7 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
     if (lane == 3 && wy < G::NTY - 1) nb_warp = warp + WPR;
     auto wait_neighbours = [&](uint32_t need) {  // all neighbours have completed phase `need`
         if (need == 0) return;
-#if GCMF_OPT_POLLWAIT
-        mbar_poll(&nbar[warp * 2 + (need & 1u)], ((need - 1u) >> 1) & 1u);
-#else
         mbar_wait(&nbar[warp * 2 + (need & 1u)], ((need - 1u) >> 1) & 1u);
-#endif
     };
     auto publish = [&](uint32_t done) {  // this warp has completed phase `done`
         __syncwarp();
@@ -1021,7 +697,7 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
     for (int64_t l = l0; l < l1; ++l, ++it) {
         const uint32_t g0 = (uint32_t)it * (uint32_t)(P.k + 1);
         tl.load_bar(tid, l, st);
-        if (KIND == FK_FLUX && it == 0) mbar_wait(&mb[0], 0);
+        if (it == 0) mbar_wait(&mb[0], 0);
         mbar_wait(&mb[1], (unsigned)(it & 1));
         // (Dropping this wait for even k -- extract only writes the thread's own points of S0, which no neighbour
         // reads after step k-1 -- is NOT safe: a neighbour could then arrive for phase g+2 on a barrier whose phase g
@@ -1030,20 +706,13 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
         tl.extract(tid, st);
         publish(g0 + 1);
         // The landing tiles are refilled for the next level once every warp has drained them (32 lanes = TH rows).
-        uint32_t old = 0;
-        if (lane == 0) old = atom_add_acqrel_u32(xcount, 1u);
+        // Warp 0 re-arms them -- an edge warp that owns halo rows only and does 6 of the inner warps' 16 row-steps per
+        // level (measured -4.4 % against "whichever warp drains them last", whose ~300 instructions of address
+        // arithmetic and copy issue landed on the critical path of a random inner warp).  It looks at the drain counter
+        // before each of its steps and, at the latest, waits for it after its last one (every other warp reaches its
+        // own extract without any further help from warp 0; model-checked in tests/tools/sync_model.py).
+        if (lane == 0) atom_add_acqrel_u32(xcount, 1u);
         const uint32_t drained = (uint32_t)NWARPS * (uint32_t)(it + 1);  // counter value when all warps are through
-        auto refill = [&]() {
-            fence_proxy_async();
-            if (lane < G::TH) {
-                tl.issue_state_row(lane, l + 1, &mb[1]);
-                mbar_expect_tx(&mb[1], tl.state_tx_bytes(lane));
-                if (GCMF_OPT_BARPF == 1) tl.prefetch_bar_row(lane, l + 1);
-            }
-        };
-#if GCMF_OPT_EDGEREFILL
-        // warp 0 re-arms them: it looks at the counter before each of its steps and, at the latest, waits for it
-        // after its last one (every other warp reaches its own extract without any further help from warp 0)
         bool refill_due = warp == 0 && l + 1 < l1;
         auto try_refill = [&](bool block) {
             if (!refill_due) return;
@@ -1053,27 +722,19 @@ __global__ void __launch_bounds__(FusedGeom<T, FusedSplit<KIND>::value>::NTHREAD
                 seen = __shfl_sync(0xffffffffu, seen, 0);
             } while (block && seen < drained);
             if (seen >= drained) {
-                refill();
+                fence_proxy_async();
+                if (lane < G::TH) tl.issue_state(lane, l + 1, &mb[1]);
                 refill_due = false;
             }
         };
-#else
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old == drained - 1u && l + 1 < l1) refill();  // the last warp through does it
-#endif
-        if (GCMF_OPT_BARPF == 2 && l + 1 < l1) tl.prefetch_bar_own(tid, l + 1);
 #pragma unroll 1
         for (int s = 1; s <= P.k; ++s) {
-#if GCMF_OPT_EDGEREFILL
             try_refill(false);
-#endif
             wait_neighbours(g0 + (uint32_t)s);
             tl.step(tid, s, st);
             publish(g0 + (uint32_t)s + 1u);
         }
-#if GCMF_OPT_EDGEREFILL
         try_refill(true);
-#endif
         tl.store(tid, l, st);
     }
     }

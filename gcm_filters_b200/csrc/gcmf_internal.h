@@ -17,6 +17,14 @@ struct gcmf_plan {
     double c;
     int sm_count;
     int steps_per_block;  // 0 = auto (fuse when eligible), 1 = never fuse, 2..4 = cap
+    // tensor maps of the arrays the fused kernels stage through the TMA engine, encoded once per distinct array
+    struct MapEntry {
+        const void* p;
+        int64_t pitch, bstride, nb;
+        gcmf::TmaDesc d;
+    };
+    std::vector<MapEntry> state_maps;   // small LRU: the recurrence rotates through <= 5 arrays
+    MapEntry coef_maps[3];              // ce, cn, ra of the FLUX family (p == nullptr: not encoded yet)
 };
 
 int gcmf_set_error(int code, const char* fmt, ...);

@@ -69,6 +69,9 @@ struct PlaneRef {
     int32_t nb;
 };
 
+// CUtensorMap (128 opaque bytes, 64-byte aligned): a TMA descriptor encoded on the host, see gcmf_fused.cuh
+struct alignas(64) TmaDesc { uint64_t opaque[16]; };
+
 template <typename T> struct FieldRef {
     T* p;
     int64_t pitch;
@@ -247,14 +250,9 @@ template <typename T> GCMF_HD T shifted_flux(T x, T c, T lap) { return fma_(-c, 
 
 // T_i = 2 A(T_{i-1}) - T_{i-2} (filter.py:197-203) as one fma: 2*a is exact, so the bits are those of (2*a) - t2.
 template <typename T> GCMF_HD T cheb_next(T a, T t2) { return fma_(T(2), a, -t2); }
-// bar + p_i T_i in fp64 (filter.py:204; 195 with bar = p0 x).  CONTRACT: one rounding (the flux family, whose parity
-// is a tolerance); otherwise numpy's two roundings (the families that are bit-exact to the reference).
-#ifndef GCMF_OPT_CONTRACT
-#define GCMF_OPT_CONTRACT 0
-#endif
-template <bool CONTRACT> GCMF_HD double bar_update(double bar, double p, double t0) {
-    return (CONTRACT && GCMF_OPT_CONTRACT) ? ::fma(p, t0, bar) : bar + p * t0;
-}
+// bar + p_i T_i in fp64 (filter.py:204; 195 with bar = p0 x): numpy's two roundings, in every kernel (contracting it
+// into one fma was measured within noise and would only move the results away from the reference's).
+GCMF_HD double bar_update(double bar, double p, double t0) { return bar + p * t0; }
 
 // exponent all ones: NaN or +-inf (what nan2num changes)
 GCMF_HD bool nonfinite(double x) {
@@ -488,7 +486,7 @@ GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&l
             if (HALO) halo_push_row<T, VX>(P, k, b, j, i0, a);
 #pragma unroll
             for (int v = 0; v < VX; ++v)  // filter.py:195
-                outv[v] = (T)bar_update<FMA_SHIFT>(P.p0 * (double)x[k][v], P.p1, (double)a[v]);
+                outv[v] = (T)bar_update(P.p0 * (double)x[k][v], P.p1, (double)a[v]);
             St<T, VX>::go(barp, outv);
         } else {
             T t2[VX], t0[VX], bar[VX];
@@ -497,7 +495,7 @@ GCMF_HD void step_tail(const StepParams<T>& P, int b, int j, int i0, const T (&l
 #pragma unroll
             for (int v = 0; v < VX; ++v) {
                 t0[v] = cheb_next<T>(a[v], t2[v]);                              // filter.py:197-203
-                outv[v] = (T)bar_update<FMA_SHIFT>((double)bar[v], P.p1, (double)t0[v]);  // filter.py:204
+                outv[v] = (T)bar_update((double)bar[v], P.p1, (double)t0[v]);  // filter.py:204
             }
             if (MODE == MODE_MID) {
                 St<T, VX>::go(P.t0[k].p + (int64_t)b * P.t0[k].bstride + (int64_t)j * P.t0[k].pitch + i0, t0);
