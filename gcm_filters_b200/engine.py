@@ -139,6 +139,35 @@ def workspace(device, nbytes):
         return t
 
 
+def fit_batch(plan, nb, device):
+    """Largest batch count <= nb whose filter workspace (2 scratch fields per component, 4 with the temporally blocked
+    kernels) fits in the device memory that is free right now: a device-resident field close to the HBM size is
+    filtered in several passes over batch slices instead of failing to allocate 4x its size."""
+    torch = _torch()
+    need = plan.lib.workspace_bytes(plan.handle, nb)
+    with _ws_lock:
+        have = _workspaces.get(device.index)
+        have_n = have.numel() if have is not None else 0
+    if need <= have_n:
+        return nb
+    free, _total = torch.cuda.mem_get_info(device)
+    free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)  # cached blocks are reusable
+    budget = int(0.9 * free) + have_n  # the old workspace is dropped before a larger one is allocated
+    if need <= budget:
+        return nb
+    return max(1, min(nb, int(budget // (need / nb))))
+
+
+def _filter_in_batches(plan, nb, dev_in, dev_out, device, stream):
+    """gcmf_filter over the whole batch, or over slices of it when the workspace would not fit (see fit_batch)."""
+    step = fit_batch(plan, nb, device)
+    ws = workspace(device, plan.lib.workspace_bytes(plan.handle, step))
+    for b0 in range(0, nb, step):
+        n = min(step, nb - b0)
+        plan.lib.filter(plan.handle, n, _specs([t[b0:b0 + n] for t in dev_in]), _specs([t[b0:b0 + n] for t in dev_out]),
+                        ws.data_ptr(), ws.numel(), stream)
+
+
 def release_workspaces():
     with _ws_lock:
         _workspaces.clear()
@@ -254,6 +283,9 @@ PIPELINE_MIN_CHUNKS = 4
 PIPELINE_TARGET_CHUNKS = int(os.environ.get("GCMF_PIPELINE_CHUNKS", "8"))
 PIPELINE_MAX_CHUNK_BYTES = 1 << 30
 PIPELINE_NBUF = 2  # device-side input / output chunk buffers in flight
+PIPELINE_CACHED_GEOMETRIES = 3
+PIPELINE_STAGE_SLOTS = 3   # pinned staging chunks per direction for pageable host arrays
+PIPELINE_COPY_THREADS = int(os.environ.get("GCMF_COPY_THREADS", "0")) or max(2, min(8, len(os.sched_getaffinity(0)) // 2))
 _pipe_lock = threading.Lock()
 _pipe_state = {}
 
@@ -324,18 +356,26 @@ def _run_filter_pipelined(lap, p, c, fields, out, shape, np_dtype):
     nbuf = PIPELINE_NBUF
     key = (device.index, str(tdt), ncomp, chunk, ny, nx, nbuf)
     with _pipe_lock:
-        stt = _pipe_state.get(key)
+        stt = _pipe_state.pop(key, None)
         if stt is None:
-            _pipe_state.clear()  # one cached pipeline geometry per process: bounded device memory
-            stt = _pipe_state[key] = {
+            # a few cached pipeline geometries per process (least recently used goes first): alternating shapes, e.g.
+            # two variables filtered in turn from dask worker threads, must not reallocate on every call
+            while len(_pipe_state) >= PIPELINE_CACHED_GEOMETRIES:
+                _pipe_state.pop(next(iter(_pipe_state)))
+            stt = {
                 "din": [[torch.empty((chunk, ny, nx), dtype=tdt, device=device) for _ in range(ncomp)] for _ in range(nbuf)],
                 "dout": [[torch.empty((chunk, ny, nx), dtype=tdt, device=device) for _ in range(ncomp)] for _ in range(nbuf)],
-                "h2d": torch.cuda.Stream(device), "d2h": torch.cuda.Stream(device),
+                "h2d": torch.cuda.Stream(device), "d2h": torch.cuda.Stream(device), "lock": threading.Lock(),
             }
-    din, dout, s_h2d, s_d2h = stt["din"], stt["dout"], stt["h2d"], stt["d2h"]
+        _pipe_state[key] = stt  # (re-)inserted last = most recently used
     s_comp = torch.cuda.current_stream(device)
-    with launch_lock(device.index):
+    staged_in = not all(h.is_pinned() for h in host_in)
+    staged_out = not all(h.is_pinned() for h in host_out)
+    with launch_lock(device.index), stt["lock"]:
         plan.set_filter(p, c)
+        if staged_in or staged_out:
+            return _pipeline_loop_staged(plan, stt, host_in, host_out, results, chunk, nb, ncomp, tdt, device, s_comp,
+                                         staged_in, staged_out)
         return _pipeline_loop(plan, stt, host_in, host_out, results, chunk, nb, ncomp, tdt, device, s_comp)
 
 
@@ -374,6 +414,149 @@ def _pipeline_loop(plan, stt, host_in, host_out, results, chunk, nb, ncomp, tdt,
         b0 += n
     s_d2h.synchronize()
     s_comp.wait_stream(s_d2h)
+    return tuple(results)
+
+
+_copy_pool = None
+
+
+def _parallel_copy(dst, src):
+    """dst[...] = src[...] between two host tensors of the same shape, split over a few threads (numpy releases the
+    GIL while it copies): one thread moves ~10 GB/s, a pageable 4 GB field each way would otherwise dominate."""
+    global _copy_pool
+    d = dst.numpy().reshape(-1)
+    s_ = src.numpy() if _is_torch(src) else src
+    s_ = s_.reshape(-1)
+    n = d.shape[0]
+    parts = PIPELINE_COPY_THREADS if n >= (1 << 20) else 1
+    if parts == 1:
+        np.copyto(d, s_, casting="unsafe")
+        return
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _copy_pool = ThreadPoolExecutor(max_workers=PIPELINE_COPY_THREADS, thread_name_prefix="gcmf-copy")
+    step = (n + parts - 1) // parts
+    futs = [_copy_pool.submit(np.copyto, d[a:a + step], s_[a:a + step], "unsafe") for a in range(0, n, step)]
+    for f in futs:
+        f.result()
+
+
+def _pipeline_loop_staged(plan, stt, host_in, host_out, results, chunk, nb, ncomp, tdt, device, s_comp, staged_in,
+                          staged_out):
+    """The chunk pipeline for PAGEABLE host arrays (plain numpy in / numpy out: what an xarray user passes).
+    cudaMemcpyAsync from / to pageable memory is synchronous and staged by the driver through one small buffer;
+    here a producer thread copies chunk i+1 of the input into a ring of pinned staging chunks while chunk i is in
+    flight, and a consumer thread copies finished chunks out of a pinned ring into the caller's array, so that H2D,
+    filter and D2H overlap exactly as they do for pinned arrays."""
+    import queue
+
+    torch = _torch()
+    nbuf = len(stt["din"])
+    din, dout, s_h2d, s_d2h = stt["din"], stt["dout"], stt["h2d"], stt["d2h"]
+    ws = workspace(device, plan.lib.workspace_bytes(plan.handle, chunk))
+    ny, nx = din[0][0].shape[-2:]
+    slots = PIPELINE_STAGE_SLOTS
+    skey = ("stage", slots, staged_in, staged_out)
+    if skey not in stt:
+        def ring():
+            return [[torch.empty((chunk, ny, nx), dtype=tdt, pin_memory=True) for _ in range(ncomp)] for _ in range(slots)]
+        stt[skey] = (ring() if staged_in else None, ring() if staged_out else None)
+    ring_in, ring_out = stt[skey]
+    sizes = _chunk_schedule(nb, chunk)
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + n)
+    nchunks = len(sizes)
+    ev_h2d = [torch.cuda.Event() for _ in range(nchunks)]
+    ev_comp = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_d2h = [torch.cuda.Event() for _ in range(nchunks)]
+    h2d_recorded = [threading.Event() for _ in range(nchunks)]
+    q_in, q_out = queue.Queue(), queue.Queue()
+    free_out = threading.Semaphore(slots)
+    errors = []
+
+    def producer():
+        try:
+            for i, n in enumerate(sizes):
+                if i >= slots:  # the H2D copy that last read this staging slot has finished
+                    h2d_recorded[i - slots].wait()
+                    ev_h2d[i - slots].synchronize()
+                for cc in range(ncomp):
+                    _parallel_copy(ring_in[i % slots][cc][:n], host_in[cc][offs[i]:offs[i] + n])
+                q_in.put(i)
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            q_in.put(-1)
+
+    def consumer():
+        try:
+            while True:
+                i = q_out.get()
+                if i is None:
+                    return
+                ev_d2h[i].synchronize()
+                n = sizes[i]
+                for cc in range(ncomp):
+                    _parallel_copy(host_out[cc][offs[i]:offs[i] + n], ring_out[i % slots][cc][:n])
+                free_out.release()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            free_out.release()
+
+    threads = []
+    if staged_in:
+        threads.append(threading.Thread(target=producer, name="gcmf-stage-in", daemon=True))
+    if staged_out:
+        threads.append(threading.Thread(target=consumer, name="gcmf-stage-out", daemon=True))
+    for t in threads:
+        t.start()
+    s_h2d.wait_stream(s_comp)
+    try:
+        for i, n in enumerate(sizes):
+            k = i % nbuf
+            b0 = offs[i]
+            if staged_in:
+                got = q_in.get()
+                if got < 0:
+                    raise errors[0]
+            with torch.cuda.stream(s_h2d):
+                if i >= nbuf:
+                    s_h2d.wait_event(ev_comp[k])  # the filter that read this input buffer has finished
+                for cc in range(ncomp):
+                    src = ring_in[i % slots][cc][:n] if staged_in else host_in[cc][b0:b0 + n]
+                    din[k][cc][:n].copy_(src, non_blocking=True)
+                ev_h2d[i].record(s_h2d)
+            h2d_recorded[i].set()
+            s_comp.wait_event(ev_h2d[i])
+            if i >= nbuf:
+                s_comp.wait_event(ev_d2h[i - nbuf])  # the previous result in this output buffer has left the device
+            plan.lib.filter(plan.handle, n, _specs([t[:n] for t in din[k]]), _specs([t[:n] for t in dout[k]]),
+                            ws.data_ptr(), ws.numel(), s_comp.cuda_stream)
+            ev_comp[k].record(s_comp)
+            if staged_out:
+                free_out.acquire()  # a pinned staging chunk is free again (back-pressure from the consumer)
+                if errors:
+                    raise errors[0]
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_comp[k])
+                for cc in range(ncomp):
+                    dst = ring_out[i % slots][cc][:n] if staged_out else host_out[cc][b0:b0 + n]
+                    dst.copy_(dout[k][cc][:n], non_blocking=True)
+                ev_d2h[i].record(s_d2h)
+            if staged_out:
+                q_out.put(i)
+    finally:
+        for ev in h2d_recorded:
+            ev.set()
+        if staged_out:
+            q_out.put(None)
+        for t in threads:
+            t.join()
+    s_d2h.synchronize()
+    s_comp.wait_stream(s_d2h)
+    if errors:
+        raise errors[0]
     return tuple(results)
 
 
@@ -426,9 +609,8 @@ def run_filter(lap, p, c, fields, out=None):
     outs = st.out_like()
     with launch_lock(st.device.index), torch.cuda.device(st.device):
         plan.set_filter(p, c)
-        ws = workspace(st.device, plan.lib.workspace_bytes(plan.handle, st.nb))
         stream = torch.cuda.current_stream(st.device).cuda_stream
-        plan.lib.filter(plan.handle, st.nb, _specs(st.dev), _specs(outs), ws.data_ptr(), ws.numel(), stream)
+        _filter_in_batches(plan, st.nb, st.dev, outs, st.device, stream)
     return st.deliver(outs, out)
 
 
@@ -442,7 +624,6 @@ def filter_device(lap, p, c, dev_in, dev_out):
     plan = device_plan(lap, t0.device.index, np_dtype, ny, nx)
     with launch_lock(t0.device.index):
         plan.set_filter(p, c)
-        ws = workspace(t0.device, plan.lib.workspace_bytes(plan.handle, nb))
         stream = torch.cuda.current_stream(t0.device).cuda_stream
-        plan.lib.filter(plan.handle, nb, _specs(dev_in), _specs(dev_out), ws.data_ptr(), ws.numel(), stream)
+        _filter_in_batches(plan, nb, dev_in, dev_out, t0.device, stream)
     return dev_out

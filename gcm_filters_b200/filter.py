@@ -99,10 +99,31 @@ def _shift_scale(filter_spec: FilterSpec, Laplacian):
     return 2 / (filter_spec.s_max * filter_spec.dx_min_sq)
 
 
+_FP_WHOLE_BYTES = 4 << 20
+_FP_ROWS = 64
+
+
+def _fingerprint(a):
+    """Cheap content fingerprint of a host array: the wrap-around sum of its 8-byte words.  Arrays up to 4 MiB are
+    summed whole (any in-place edit shows); larger ones are sampled on 64 evenly spaced rows, first and last included
+    (~0.3 ms for a 69 MB plane -- the check runs on every filter call).  Call ``Filter.invalidate_grid_cache()`` after
+    editing a large grid variable in place if the edit may fall between the sampled rows."""
+    if a.nbytes > _FP_WHOLE_BYTES and a.ndim >= 2:
+        rows = a.reshape((-1, a.shape[-1])) if a.flags.c_contiguous else a.reshape((-1, a.shape[-1]))
+        idx = np.unique(np.linspace(0, rows.shape[0] - 1, _FP_ROWS).astype(np.int64))
+        a = rows[idx]
+    a = np.ascontiguousarray(a)
+    raw = a.reshape(-1).view(np.uint8)
+    n8 = raw.shape[0] // 8 * 8
+    total = int(raw[:n8].view(np.uint64).sum(dtype=np.uint64)) if n8 else 0
+    return (total + int(raw[n8:].sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+
+
 class _LaplacianCache:
-    """Laplacian objects (validated + precombined + uploaded planes) keyed by the identity of the
-    grid arrays, so repeated calls / dask blocks do not rebuild them as the reference does
-    (filter.py:183).  Arrays are kept alive by the cache; mutate grid arrays in place at your peril."""
+    """Laplacian objects (validated + precombined + uploaded planes) so that repeated calls / dask blocks do not
+    rebuild them as the reference does on every call (filter.py:183).  Keyed by the identity AND a content fingerprint
+    of the grid arrays: an in-place edit of a grid variable between two calls rebuilds the operator, as the reference
+    would.  The cache keeps the (converted) arrays alive, so an address cannot be recycled by a different array."""
 
     def __init__(self, Laplacian, size=4):
         self.Laplacian = Laplacian
@@ -111,19 +132,24 @@ class _LaplacianCache:
 
     @staticmethod
     def _key(a):
+        """(key, array to keep alive)"""
         if engine._is_torch(a):
-            return ("t", a.data_ptr(), tuple(a.shape), str(a.dtype), tuple(a.stride()), a._version)
-        a = np.asarray(getattr(a, "values", a))
-        return ("n", a.__array_interface__["data"][0], a.shape, a.dtype.str, a.strides)
+            return ("t", a.data_ptr(), tuple(a.shape), str(a.dtype), tuple(a.stride()), a._version), a
+        arr = np.asarray(getattr(a, "values", a))
+        return ("n", arr.__array_interface__["data"][0], arr.shape, arr.dtype.str, arr.strides, _fingerprint(arr)), arr
+
+    def clear(self):
+        self.entries = []
 
     def get(self, args):
-        key = tuple(self._key(a) for a in args)
+        keyed = [self._key(a) for a in args]
+        key = tuple(k for k, _ in keyed)
         for k, keep, lap in self.entries:
             if k == key:
                 return lap
         names = self.Laplacian.required_grid_args()
         lap = self.Laplacian(**dict(zip(names, args)))
-        self.entries.append((key, args, lap))
+        self.entries.append((key, (args, [arr for _, arr in keyed]), lap))
         if len(self.entries) > self.size:
             self.entries.pop(0)
         return lap
@@ -241,27 +267,17 @@ class Filter:
         args = [self.grid_ds[name] for name in self.Laplacian.required_grid_args()]
         return self._cache.get(tuple(args))
 
-    def plot_shape(self, ax=None):
-        """Plot the target filter and its polynomial approximation (reference filter.py:395-428)."""
-        import matplotlib.pyplot as plt
+    def invalidate_grid_cache(self):
+        """Forget the cached Laplacian operators (validated, precombined and uploaded grid variables).  Only needed
+        after editing a LARGE grid variable in place between two calls (see ``_fingerprint``); the reference rebuilds
+        its Laplacian on every call (filter.py:183)."""
+        self._cache.clear()
 
-        s_max = self.filter_spec.s_max
-        F = _target_function[self.filter_shape](TargetSpec(s_max, self.filter_scale, self.transition_width))
-        x = np.linspace(-1, 1, 10001)
-        k = np.sqrt(s_max * (x + 1) / 2)
-        if ax is None:
-            _, ax = plt.subplots()
-        ax.plot(k, F(x), "g", label="target filter", linewidth=4)
-        ax.plot(k, np.polynomial.chebyshev.chebval(x, self.filter_spec.p), "m", label="approximation", linewidth=4)
-        ax.axvline(2 * np.pi / self.filter_scale, color="k", label="filter cutoff wavenumber", linewidth=2)
-        ax.set_xlim(left=0)
-        if self.filter_scale / self.dx_min > 10:
-            ax.set_xlim(right=4 * np.pi / self.filter_scale)
-        ax.set_ylim(bottom=-0.1)
-        ax.set_ylim(top=1.1)
-        ax.set_xlabel("Wavenumber k", fontsize=18)
-        ax.grid(True)
-        ax.legend()
+    def plot_shape(self, ax=None):
+        """Not part of the filter path (reference filter.py:395-428, matplotlib only): out of scope here, see
+        DESIGN.md section 8.  ``filter_spec.p`` holds the Chebyshev coefficients a plot would evaluate."""
+        raise NotImplementedError("plot_shape is outside the scope of gcm_filters_b200 (the iterative filter path); "
+                                  "use the reference package to plot the target filter")
 
     # --------------------------------------------------------------------------------------
     def apply(self, ds, dims=None, out=None):

@@ -285,13 +285,23 @@ class PeerBandedFilter(BandedFilter):
 
         if nbytes in self._buffers:  # one allocation (and one rendezvous) per geometry
             t, ptrs = self._buffers[nbytes]
-            t.zero_()
-            self._epoch = 0
             if self.memory != "local":
                 import torch.distributed as dist
 
+                # Order matters: a rank's last step only waits for its neighbours' previous step, so a neighbour's
+                # final kernel may still be signalling into my flag words when I get here.  Everybody first finishes
+                # its own kernels and meets at the barrier -- nobody is writing into anybody's buffer any more -- and
+                # only then are the flags and ghost rows cleared and the epoch reset; a second barrier keeps a fast
+                # rank from pushing into a buffer that a slow rank has not cleared yet.
                 torch.cuda.synchronize(self.device)
-                dist.barrier(group=self.group)  # nobody may still be signalling into the old contents
+                dist.barrier(group=self.group)
+                t.zero_()
+                self._epoch = 0
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)
+            else:
+                t.zero_()
+                self._epoch = 0
             return t, ptrs
         if self.memory == "local":
             assert self.world == 1, "local memory only supports a single rank (its own neighbour)"
@@ -477,7 +487,12 @@ class FusedBandedFilter(BandedFilter):
                 hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
                 self._symm = ((tdt, slab), buf, hdl)
             _, buf, hdl = self._symm
+            # a neighbour's pull copies of the previous apply() may still be reading my arrays: meet first, then clear
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
             buf.zero_()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
             arrays = [buf[k * slab:(k + 1) * slab].view(1, nb, rows, nx) for k in range(n_arrays)]
             north, south = (self.rank + 1) % self.world, (self.rank - 1) % self.world
             peers = dict(hdl=hdl, nyl_south=bands[south][1] - bands[south][0],

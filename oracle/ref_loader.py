@@ -15,15 +15,28 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("GCMF_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# where an UNMODIFIED copy of the reference package may live: an explicit override, the build container's read-only
+# tree, or the `pip install --target baseline/_ref /root/reference` copy that travels to the GPU box (git-ignored)
+CANDIDATES = [os.environ.get("GCMF_REFERENCE"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
 
 
 class ReferenceUnavailable(RuntimeError):
     pass
 
 
+def reference_root():
+    for root in CANDIDATES:
+        if root and os.path.isfile(os.path.join(root, "gcm_filters", "kernels.py")):
+            return root
+    return None
+
+
+REFERENCE_ROOT = reference_root() or "/root/reference"
+
+
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "gcm_filters", "kernels.py"))
+    return reference_root() is not None
 
 
 def _xarray_stub():
@@ -49,16 +62,17 @@ def load():
     global _ref
     if _ref is not None:
         return _ref
-    if not available():
-        raise ReferenceUnavailable(f"no reference tree at {REFERENCE_ROOT}")
+    root = reference_root()
+    if root is None:
+        raise ReferenceUnavailable(f"no reference tree in {[c for c in CANDIDATES if c]}")
     sys.dont_write_bytecode = True  # the tree is read-only
     if "xarray" not in sys.modules:
         try:
             importlib.import_module("xarray")
         except ImportError:
             sys.modules["xarray"] = _xarray_stub()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     _ref = importlib.import_module("gcm_filters")
     return _ref
 

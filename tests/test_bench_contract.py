@@ -20,7 +20,10 @@ def test_reference_arm_prints_one_json_line():
                 "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["value"] > 0 and d["vs_baseline"] is None and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    # "reference" where the unmodified reference package is importable (build container: /root/reference; GPU box:
+    # baseline/_ref), else the oracle port
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["sample"] and d["steps"] == 1 and d["warmup"] == 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
@@ -28,7 +31,7 @@ def test_gpu_arm_does_not_import_the_oracle():
     """Only the cpu_baseline / reference legs of bench.py may touch oracle/ (the synthetic inputs come from
     bench_inputs.py)."""
     src = open(os.path.join(ROOT, "bench.py")).read()
-    gpu_arm = src[src.index("def gpu_arm("):src.index("# ------------------------------------------------------------------------------------------ banded arm")]
+    gpu_arm = src[src.index("# ------------------------------------------------------------------------------------------ GPU arm"):src.index("# ------------------------------------------------------------------------------------------ banded arm")]
     banded = src[src.index("def banded_arm("):src.index("# ------------------------------------------------------------------------------------------ reference arm")]
     assert "oracle" not in gpu_arm.replace("cpu_baseline", "") and "oracle" not in banded
     pkg = os.path.join(ROOT, "gcm_filters_b200")

@@ -80,15 +80,20 @@ def _worker(rank, world, port, g, shape, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("g", ["IRREGULAR_WITH_LAND", "TRIPOLAR_POP_WITH_LAND", "VECTOR_C_GRID"])
-def test_banded_and_sharded_match_single_gpu(g):
+def test_banded_and_sharded_match_single_gpu(g, world):
+    """Bands of 48 (45) rows per GPU: BandedFilter (NCCL per step), PeerBandedFilter (flag-synchronised stores into
+    peer memory, three epochs on reused symmetric buffers), FusedBandedFilter with both exchanges, batch sharding --
+    all against the single-GPU one-step kernels, bit for bit."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, g, (90, 160) if g == "VECTOR_C_GRID" else (96, 264), q))
+    shape = (45 * world, 160) if g == "VECTOR_C_GRID" else (48 * world, 264)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, g, shape, q))
              for r in range(world)]
     for p in procs:
         p.start()
