@@ -278,6 +278,108 @@ __global__ void __launch_bounds__(CgridTile<T>::NTHREADS, GCMF_CGRID_MINBLOCKS) 
     if (HALO) halo_signal<T>(P.halo, bottom, top, nxb * nbu);
 }
 
+// VECTOR_C, row-marching form (the default).  A warp owns CG_COLS = 30 output columns (lanes 1..30; lanes 0 and 31 carry
+// the west / east neighbour column) and marches north through a band of rows, one row per iteration, keeping in
+// registers everything of row j that row j+1 needs again: the point products b = v/dxCv, c = v/dyCv, e = u/dxCu, the raw
+// (u, v), the four reciprocal spacings, the weighted stresses dyT^2*sxx, dxT^2*sxx of row j and dxBu^2*sxy of row j-1.
+// West / east neighbours come from the adjacent lanes (four fp64 shuffles per row).  Every field and coefficient value
+// is loaded from memory ONCE per output point (plus one priming row per band and two halo lanes per warp): 160 B read
+// + 32 B written per point-step = B_alg, where the tiled kernel re-read ~24 values per stress entry through L1 with
+// ~300 instructions of 64-bit address arithmetic and spilled at its 40-register cap.  Same expressions in the same
+// order as OpVectorC / CgridTile (kernels.py:647-696): results are bit-identical.
+constexpr int CG_WARPS = 4;   // warps per CTA: neighbouring column tiles of one row band (their halo columns hit in L1)
+constexpr int CG_COLS = 30;   // output columns per warp
+#ifndef GCMF_CGM_MINBLOCKS
+#define GCMF_CGM_MINBLOCKS 4  // 127 registers, no spills, 16 warps per SM: A/B on cfg5 (ms per step) 1: 0.501, 4: 0.389, 6: 0.520, 8: 0.433
+#endif
+// read-only loads (ld.global.nc): the inputs of a step are never written by it, so the compiler may hoist the next
+// row's loads above the current row's stores (GCMF_CGM_LDG=0: plain loads, ordered with the stores)
+#ifndef GCMF_CGM_LDG
+#define GCMF_CGM_LDG 1
+#endif
+#if GCMF_CGM_LDG
+#define LDRO(p) __ldg(p)
+#else
+#define LDRO(p) (*(p))
+#endif
+template <typename T, int MODE, bool HALO>
+__global__ void __launch_bounds__(32 * CG_WARPS, GCMF_CGM_MINBLOCKS) cgrid_march_kernel(const __grid_constant__ StepParams<T> P, unsigned ctas_x,
+                                                                   int ry) {
+    unsigned bid = blockIdx.x;
+    const unsigned cx = bid % ctas_x;
+    bid /= ctas_x;
+    const unsigned nbu = (unsigned)P.nb;
+    const int b = (int)(bid % nbu);
+    const int band = (int)(bid / nbu);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ny = P.g.ny, nx = P.g.nx;
+    const int j0 = band * ry, j1 = j0 + ry < ny ? j0 + ry : ny;
+    const bool bottom = j0 == 0, top = j1 >= ny;
+    if (HALO) halo_wait<T>(P.halo, bottom, top);
+    const int i = (int)(cx * CG_WARPS + warp) * CG_COLS + lane - 1;  // may be -1 or >= nx: wrapped once (nx >= 32)
+    const bool active = (int)(cx * CG_WARPS + warp) * CG_COLS < nx;
+    if (active) {
+        const int ic = i < 0 ? i + nx : (i >= nx ? i - nx : i);
+        const bool wrap = (P.g.flags & FL_WRAP_Y) != 0;
+        const T* U = P.t1[0].p + (int64_t)b * P.t1[0].bstride + ic;
+        const T* V = P.t1[1].p + (int64_t)b * P.t1[1].bstride + ic;
+        const int64_t fp = P.t1[0].pitch, pp = P.plane[0].pitch;
+        const T* K[14];
+#pragma unroll
+        for (int s = 0; s < 14; ++s) K[s] = plane_base<T>(P.plane[s], b) + ic;
+        const bool emit_lane = lane >= 1 && lane <= CG_COLS && i < nx;
+        // row r of the arrays (periodic y, or ghost rows -1 / ny present in memory for a latitude band)
+        auto rowidx = [&](int r) { return wrap ? (r < 0 ? r + ny : (r >= ny ? r - ny : r)) : r; };
+        // state of "row j"
+        T u_j, v_j, b_j, c_j, e_j, k0_j, k1_j, k2_j, k3_j, p1_j = T(0), p2_j = T(0), p3_jm = T(0);
+        {
+            const int64_t r = rowidx(j0 - 1);
+            u_j = LDRO(U + r * fp);
+            v_j = LDRO(V + r * fp);
+            k0_j = LDRO(K[0] + r * pp); k1_j = LDRO(K[1] + r * pp); k2_j = LDRO(K[2] + r * pp); k3_j = LDRO(K[3] + r * pp);
+            const T zu = nan2num(u_j), zv = nan2num(v_j);
+            b_j = zv * k1_j; c_j = zv * k2_j; e_j = zu * k3_j;
+        }
+        for (int j = j0 - 1; j < j1; ++j) {
+            const int64_t rn = rowidx(j + 1), rj = rowidx(j);
+            // row j+1: raw values, reciprocal spacings, point products (kernels.py:653-656, 663-666)
+            const T u_n = LDRO(U + rn * fp), v_n = LDRO(V + rn * fp);
+            const T k0_n = LDRO(K[0] + rn * pp), k1_n = LDRO(K[1] + rn * pp), k2_n = LDRO(K[2] + rn * pp), k3_n = LDRO(K[3] + rn * pp);
+            const T k4 = LDRO(K[4] + rn * pp), k5 = LDRO(K[5] + rn * pp), k8 = LDRO(K[8] + rn * pp), k9 = LDRO(K[9] + rn * pp);
+            const T k6 = LDRO(K[6] + rj * pp), k7 = LDRO(K[7] + rj * pp), k10 = LDRO(K[10] + rj * pp), k11 = LDRO(K[11] + rj * pp);
+            const T zu = nan2num(u_n), zv = nan2num(v_n);
+            const T a_n = zu * k0_n, b_n = zv * k1_n, c_n = zv * k2_n, e_n = zu * k3_n;
+            // str_xx at T point (j+1, i)  (kernels.py:653-661)
+            const T a_w = __shfl_up_sync(0xffffffffu, a_n, 1);
+            const T sxx = -(k4 * (a_n - a_w) - k5 * (b_n - b_j));
+            const T p1_n = k8 * sxx, p2_n = k9 * sxx;   // dy2h * sxx, dx2h * sxx
+            // str_xy at q point (j, i)  (kernels.py:663-670)
+            const T c_e = __shfl_down_sync(0xffffffffu, c_j, 1);
+            const T sxy = -(k6 * (c_e - c_j) + k7 * (e_n - e_j));
+            const T p3_j = k10 * sxy, p4_j = k11 * sxy;  // dx2q * sxy, dy2q * sxy
+            const T p1_e = __shfl_down_sync(0xffffffffu, p1_j, 1);
+            const T p4_w = __shfl_up_sync(0xffffffffu, p4_j, 1);
+            if (j >= j0 && emit_lane) {  // divergence at (j, i)  (kernels.py:672-694)
+                T lap[2][1], x[2][1];
+                T uc = k0_j * (p1_j - p1_e);
+                uc = uc + k3_j * (p3_jm - p3_j);
+                lap[0][0] = uc * LDRO(K[12] + rj * pp);
+                T vc = k2_j * (p4_w - p4_j);
+                vc = vc - k1_j * (p2_j - p2_n);
+                lap[1][0] = vc * LDRO(K[13] + rj * pp);
+                x[0][0] = u_j;
+                x[1][0] = v_j;
+                step_tail<T, 1, 2, false, MODE, HALO>(P, b, j, i, lap, x);
+            }
+            u_j = u_n; v_j = v_n; b_j = b_n; c_j = c_n; e_j = e_n;
+            k0_j = k0_n; k1_j = k1_n; k2_j = k2_n; k3_j = k3_n;
+            p1_j = p1_n; p2_j = p2_n; p3_jm = p3_j;
+        }
+    }
+    if (HALO) halo_signal<T>(P.halo, bottom, top, ctas_x * nbu);
+}
+
+#undef LDRO
 // Copy my first / last owned rows of a field into the neighbours' ghost rows and raise their flags (the
 // exchange of the prepared input before step 1).  One CTA column per x-block; grid (nxb, nb).
 template <typename T>
@@ -372,7 +474,50 @@ template <typename T, int MODE> static int launch_cgrid(const StepParams<T>& P, 
 #endif
 }
 
-template <typename T> static int launch_cgrid_mode(const StepParams<T>& P, int mode, cudaStream_t st) {
+#ifndef GCMF_HOSTEMU
+template <typename T, int MODE> static int launch_cgrid_march(const gcmf_plan* pl, const StepParams<T>& P, cudaStream_t st) {
+    const int nxt = (P.g.nx + CG_COLS - 1) / CG_COLS;
+    const int ctas_x = (nxt + CG_WARPS - 1) / CG_WARPS;
+    // rows per band: long enough to amortise the priming row of a band, short enough for ~16 CTAs per SM
+    const int64_t target = (int64_t)pl->sm_count * 16;
+    int64_t nbands = (target + (int64_t)ctas_x * P.nb - 1) / ((int64_t)ctas_x * P.nb);
+    if (nbands < 1) nbands = 1;
+    int ry = (int)((P.g.ny + nbands - 1) / nbands);
+    if (const char* e = getenv("GCMF_CGRID_ROWS")) {
+        const int v = atoi(e);
+        if (v > 0) ry = v;
+    } else {
+        ry = ry < 8 ? 8 : (ry > 64 ? 64 : ry);
+    }
+    nbands = (P.g.ny + ry - 1) / ry;
+    const int64_t nblk = (int64_t)ctas_x * P.nb * nbands;
+    if (nblk > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "grid too large (%lld blocks)", (long long)nblk);
+    if (P.halo.enabled)
+        cgrid_march_kernel<T, MODE, true><<<(unsigned)nblk, 32 * CG_WARPS, 0, st>>>(P, (unsigned)ctas_x, ry);
+    else
+        cgrid_march_kernel<T, MODE, false><<<(unsigned)nblk, 32 * CG_WARPS, 0, st>>>(P, (unsigned)ctas_x, ry);
+    gcmf_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCMF_OK;
+}
+#endif
+
+template <typename T> static int launch_cgrid_mode(const gcmf_plan* pl, const StepParams<T>& P, int mode, cudaStream_t st) {
+#ifndef GCMF_HOSTEMU
+    // the marching kernel wraps column indices once: grids at least one warp wide; the tiled kernel covers the rest
+    // (and is the emulator's form of the operator: bit-identical, checked on the GPU by tests/cabi/gpu_vs_emu.c)
+    static const bool tiled = getenv("GCMF_CGRID_TILED") != nullptr;
+    if (!tiled && P.g.nx >= 32) {
+        switch (mode) {
+            case MODE_LAP: return launch_cgrid_march<T, MODE_LAP>(pl, P, st);
+            case MODE_FIRST: return launch_cgrid_march<T, MODE_FIRST>(pl, P, st);
+            case MODE_MID: return launch_cgrid_march<T, MODE_MID>(pl, P, st);
+            case MODE_LAST: return launch_cgrid_march<T, MODE_LAST>(pl, P, st);
+        }
+    }
+#else
+    (void)pl;
+#endif
     switch (mode) {
         case MODE_LAP: return launch_cgrid<T, MODE_LAP>(P, st);
         case MODE_FIRST: return launch_cgrid<T, MODE_FIRST>(P, st);
@@ -409,7 +554,7 @@ static int launch_op(const gcmf_plan* pl, const StepParams<T>& P, int mode, cuda
             // tiled kernel needs every neighbour inside the array: at least 2 rows/columns; the point-wise
             // OpVectorC kernel remains for degenerate grids (and as the test oracle of the tiled one)
             static const bool pointwise = getenv("GCMF_CGRID_POINTWISE") != nullptr;
-            if (!pointwise && P.g.ny >= 2 && P.g.nx >= 2) return launch_cgrid_mode<T>(P, mode, st);
+            if (!pointwise && P.g.ny >= 2 && P.g.nx >= 2) return launch_cgrid_mode<T>(pl, P, mode, st);
             return launch_mode<T, 1, OpVectorC<T, 1>>(P, mode, st);
         }
     }

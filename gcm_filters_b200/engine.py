@@ -25,6 +25,43 @@ def set_steps_per_block(k):
     STEPS_PER_BLOCK = int(k)
 
 
+# In-process multi-GPU scheduling of host-resident batches (the role of dask="parallelized" over batch dims in the
+# reference, filter.py:478-486): None = the current device only; a list of device indices = the batch is cut into
+# contiguous slabs, one per device, each streamed through its device's copy / filter / copy pipeline by a host thread.
+DEVICES = None
+
+
+def set_devices(devices):
+    """``None`` / ``"current"``: filter on the current CUDA device (default).  ``"all"`` or a list of device indices:
+    ``Filter.apply`` / ``apply_to_vector`` on HOST arrays (numpy, CPU tensors) shard the flattened batch dimension over
+    these devices in-process (one host thread per device, no collective).  Also settable as GCMF_DEVICES=all|0,1,..."""
+    global DEVICES
+    if devices is None or devices == "current":
+        DEVICES = None
+        return
+    torch = _torch()
+    if devices == "all":
+        devices = list(range(torch.cuda.device_count()))
+    devices = [int(d) for d in devices]
+    if not devices or any(d < 0 or d >= torch.cuda.device_count() for d in devices):
+        raise ValueError(f"bad device list {devices} ({torch.cuda.device_count()} CUDA device(s) present)")
+    DEVICES = devices if len(devices) > 1 else None
+    if len(devices) == 1:
+        torch.cuda.set_device(devices[0])
+
+
+def batch_slabs(nb, world):
+    """Contiguous slabs of the flattened batch index: sizes differ by at most one (62 levels on 8 GPUs ->
+    8,8,8,8,8,8,7,7).  Returns a list of (start, stop)."""
+    base, extra = divmod(int(nb), int(world))
+    out, start = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((start, start + n))
+        start += n
+    return out
+
+
 def _torch():
     import torch
 
@@ -597,9 +634,69 @@ def run_area_op(lap, field, divide):
     return st.deliver(outs)[0]
 
 
-def run_filter(lap, p, c, fields, out=None):
+def _devices_from_env():
+    global DEVICES
+    env = os.environ.get("GCMF_DEVICES")
+    if env and DEVICES is None:
+        set_devices("all" if env.strip() == "all" else [int(v) for v in env.split(",") if v.strip()])
+        os.environ.pop("GCMF_DEVICES", None)
+
+
+def _run_filter_multi_device(lap, p, c, fields, out, devices):
+    """Host-resident batch sharded over several devices of this process: slab r of the flattened batch goes through
+    device r's pipeline from its own host thread; results land in one output array.  No collective."""
+    torch = _torch()
+    f0 = fields[0]
+    shape = tuple(f0.shape)
+    ny, nx = shape[-2:]
+    nb = int(np.prod(shape[:-2]))
+    np_dtype = lap.compute_dtype(_float_dtype_of(f0))
+    tdt = torch.float32 if np_dtype == np.float32 else torch.float64
+    host_in = [_host_view(f, nb, ny, nx) for f in fields]
+    kind_numpy = not _is_torch(f0)
+    if out is not None:
+        outs = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+        results = list(outs)
+        host_out = []
+        for o in outs:
+            t = o if _is_torch(o) else torch.from_numpy(o)
+            if tuple(t.shape) != shape or not t.is_contiguous() or t.dtype != tdt:
+                raise ValueError(f"`out` must be a C-contiguous {tdt} array with the shape of the input field")
+            host_out.append(t.reshape((nb, ny, nx)))
+    else:
+        pin = _is_torch(f0) and f0.is_pinned()
+        host_out = [torch.empty((nb, ny, nx), dtype=tdt, pin_memory=pin) for _ in range(lap.ncomp)]
+        results = [h.reshape(shape).numpy() if kind_numpy else h.reshape(shape) for h in host_out]
+    slabs = [(d, a, b) for d, (a, b) in zip(devices, batch_slabs(nb, len(devices))) if b > a]
+    errors = []
+
+    def work(d, a, b):
+        try:
+            torch.cuda.set_device(d)
+            run_filter(lap, p, c, tuple(h[a:b] for h in host_in), out=tuple(h[a:b] for h in host_out), _devices=())
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=sl, name=f"gcmf-dev{sl[0]}", daemon=True) for sl in slabs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return tuple(results)
+
+
+def run_filter(lap, p, c, fields, out=None, _devices=None):
     """filtered = filter_func(fields) on the GPU: prepare, n_steps Chebyshev steps, finalize."""
     torch = _torch()
+    _devices_from_env()
+    devices = DEVICES if _devices is None else _devices
+    f0 = fields[0]
+    if devices and len(devices) > 1 and len(f0.shape) > 2 and not (_is_torch(f0) and f0.device.type != "cpu") and \
+            len(fields) == lap.ncomp and int(np.prod(f0.shape[:-2])) >= 2 and \
+            not any(np.ndim(pl) > 2 for pl in list(lap._planes.planes) + [lap._planes.mask] if pl is not None):
+        return _run_filter_multi_device(lap, p, c, fields, out, devices)
     piped = _wants_pipeline(lap, fields, out)
     if piped is not None:
         return _run_filter_pipelined(lap, p, c, fields, out, *piped)

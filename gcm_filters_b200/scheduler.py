@@ -31,16 +31,7 @@ from .filter import _shift_scale
 _AREA_FLAG = _cabi.FLAG_AREA
 
 
-def batch_slabs(nb, world):
-    """Contiguous slabs of the flattened batch index: sizes differ by at most one (62 levels on 8 GPUs ->
-    8,8,8,8,8,8,7,7).  Returns a list of (start, stop)."""
-    base, extra = divmod(int(nb), int(world))
-    out, start = [], 0
-    for r in range(world):
-        n = base + (1 if r < extra else 0)
-        out.append((start, start + n))
-        start += n
-    return out
+batch_slabs = engine.batch_slabs  # contiguous slabs of the flattened batch index, sizes differ by at most one
 
 
 def band_rows(ny, world):

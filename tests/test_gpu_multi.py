@@ -102,3 +102,30 @@ def test_banded_and_sharded_match_single_gpu(g, world):
         assert p.exitcode == 0
     res = [q.get(timeout=10) for _ in range(world)]
     assert all(r[1] and r[2] for r in res), res
+
+
+def test_in_process_sharding_over_all_devices():
+    """set_devices("all"): Filter.apply on a host batch is cut into slabs, one per GPU of this process (host threads,
+    no torchrun); same bits as the single-device call, for numpy in / numpy out and for pinned tensors with out=."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch
+    import gcm_filters_b200 as gf
+    from oracle import fixtures
+    (f,), gv = fixtures.fixture("IRREGULAR_WITH_LAND", (96, 264))
+    rng = np.random.default_rng(4)
+    fb = f[None] * (1 + 0.2 * rng.standard_normal((4 * n + 3, 1, 1)))
+    fb[:, gv["wet_mask"] == 0] = np.nan
+    flt = gf.Filter(filter_scale=8.0, dx_min=1.0, grid_type=gf.GridType.IRREGULAR_WITH_LAND, grid_vars=gv)
+    single = flt.apply(fb, None)
+    try:
+        gf.set_devices("all")
+        multi = flt.apply(fb, None)
+        pin_in = torch.from_numpy(fb).pin_memory()
+        pin_out = torch.empty_like(pin_in).pin_memory()
+        flt.apply(pin_in, None, out=pin_out)
+    finally:
+        gf.set_devices(None)
+    assert isinstance(multi, np.ndarray) and np.array_equal(multi, single, equal_nan=True)
+    assert np.array_equal(pin_out.numpy(), single, equal_nan=True)

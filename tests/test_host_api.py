@@ -18,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_public_names():
-    assert set(gf.__all__) == {"Filter", "FilterShape", "GridType", "required_grid_vars"}
+    # the reference's four names (gcm_filters/__init__.py:11-15) + the device-list knob it has no counterpart for
+    assert set(gf.__all__) == {"Filter", "FilterShape", "GridType", "required_grid_vars", "set_devices"}
     assert [g.name for g in GridType] == [
         "REGULAR", "REGULAR_AREA_WEIGHTED", "REGULAR_WITH_LAND", "REGULAR_WITH_LAND_AREA_WEIGHTED",
         "IRREGULAR_WITH_LAND", "MOM5U", "MOM5T", "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED",
