@@ -287,6 +287,11 @@ __global__ void __launch_bounds__(CgridTile<T>::NTHREADS, GCMF_CGRID_MINBLOCKS) 
 // + 32 B written per point-step = B_alg, where the tiled kernel re-read ~24 values per stress entry through L1 with
 // ~300 instructions of 64-bit address arithmetic and spilled at its 40-register cap.  Same expressions in the same
 // order as OpVectorC / CgridTile (kernels.py:647-696): results are bit-identical.
+// Band order of a launch that exchanges ghost rows (HALO): the bottom band first, the TOP band second -- both raise the
+// neighbours' flags, and the neighbours' first CTAs of the next step wait for them -- then the interior bands.
+__device__ __forceinline__ int halo_band_order(int raw, int nbands) {
+    return raw == 0 ? 0 : (raw == 1 ? nbands - 1 : raw - 1);
+}
 constexpr int CG_WARPS = 4;   // warps per CTA: neighbouring column tiles of one row band (their halo columns hit in L1)
 constexpr int CG_COLS = 30;   // output columns per warp
 #ifndef GCMF_CGM_MINBLOCKS
@@ -310,9 +315,9 @@ __global__ void __launch_bounds__(32 * CG_WARPS, GCMF_CGM_MINBLOCKS) cgrid_march
     bid /= ctas_x;
     const unsigned nbu = (unsigned)P.nb;
     const int b = (int)(bid % nbu);
-    const int band = (int)(bid / nbu);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ny = P.g.ny, nx = P.g.nx;
+    const int band = HALO ? halo_band_order((int)(bid / nbu), (ny + ry - 1) / ry) : (int)(bid / nbu);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j0 = band * ry, j1 = j0 + ry < ny ? j0 + ry : ny;
     const bool bottom = j0 == 0, top = j1 >= ny;
     if (HALO) halo_wait<T>(P.halo, bottom, top);
@@ -380,6 +385,184 @@ __global__ void __launch_bounds__(32 * CG_WARPS, GCMF_CGM_MINBLOCKS) cgrid_march
 }
 
 #undef LDRO
+// VECTOR_C, TMA-pipelined row streaming (the default for 16-byte aligned arrays).  ncu of the marching kernel above:
+// 89 % of the warp stalls are long_scoreboard, DRAM at 54 % -- its loads live in registers, so the bytes in flight are
+// capped by the register file (16 warps x 24 loads).  Here the loads live in shared memory instead: a producer lane
+// streams whole rows of all 20 arrays of a step (u, v, the 14 coefficient planes, T_{i-2} and bar of both components;
+// 240 output columns + an aligned halo) through a 5-deep ring with the TMA engine (cp.async.bulk -> UBLKCP, one copy per
+// array and row, mbarrier complete_tx), three rows ahead of the eight consumer warps, which run the marching
+// recurrence of cgrid_march_kernel on shared-memory reads and release a row's slot through an "empty" mbarrier.
+// ~117 KB in flight per SM, no register cost.  Same expressions and order: bit-identical results.
+constexpr int CGT_WARPS = 8;                  // consumer warps per CTA (+ 1 producer warp)
+constexpr int CGT_COLS = CGT_WARPS * CG_COLS; // 240 output columns per CTA
+template <typename T> struct CgtGeom {
+    static constexpr int AV = 16 / (int)sizeof(T);       // elements per 16 bytes
+    static constexpr int HALO = AV;                      // aligned halo columns on either side (one is needed)
+    static constexpr int LW = CGT_COLS + 2 * HALO;       // staged columns per row: 244 (f64) / 248 (f32)
+    static constexpr int NARR = 20;                      // u, v, K0..K13, t2u, t2v, bar_u, bar_v
+    static constexpr int STAGE_ELEMS = NARR * LW;
+    static constexpr int STAGES = 5;
+    static constexpr size_t smem_bytes() { return (size_t)STAGES * STAGE_ELEMS * sizeof(T) + 2 * STAGES * sizeof(uint64_t) + 128; }
+};
+
+template <typename T, int MODE, bool HALO>
+__device__ __forceinline__ void cgt_tail(const StepParams<T>& P, int b, int j, int i, const T (&lap)[2], const T (&x)[2],
+                                         const T (&t2)[2], const T (&bar)[2]) {
+    const T c = (T)P.c;  // same arithmetic as step_tail (filter.py:225-283), operands already in registers
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        T* t0p = P.t0[k].p + (int64_t)b * P.t0[k].bstride + (int64_t)j * P.t0[k].pitch + i;
+        if (MODE == MODE_LAP) {
+            *t0p = lap[k];
+            continue;
+        }
+        const T a = -x[k] - c * lap[k];  // shifted Laplacian, filter.py:232-236
+        T* barp = P.bar[k].p + (int64_t)b * P.bar[k].bstride + (int64_t)j * P.bar[k].pitch + i;
+        if (MODE == MODE_FIRST) {
+            *t0p = a;
+            if (HALO) { const T v1[1] = {a}; halo_push_row<T, 1>(P, k, b, j, i, v1); }
+            *barp = (T)bar_update(P.p0 * (double)x[k], P.p1, (double)a);
+        } else {
+            const T t0 = cheb_next<T>(a, t2[k]);
+            if (MODE == MODE_MID) {
+                *t0p = t0;
+                if (HALO) { const T v1[1] = {t0}; halo_push_row<T, 1>(P, k, b, j, i, v1); }
+            }
+            *barp = (T)bar_update((double)bar[k], P.p1, (double)t0);
+        }
+    }
+}
+
+template <typename T, int MODE, bool HALO>
+__global__ void __launch_bounds__(32 * (CGT_WARPS + 1), 1) cgrid_tma_kernel(const __grid_constant__ StepParams<T> P,
+                                                                            unsigned ctas_x, int ry) {
+    using G = CgtGeom<T>;
+    constexpr int NA = (MODE == MODE_MID || MODE == MODE_LAST) ? 20 : 16;  // arrays of a full row
+    extern __shared__ __align__(128) unsigned char cgt_smem[];
+    T* ring = reinterpret_cast<T*>(cgt_smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(cgt_smem + (size_t)G::STAGES * G::STAGE_ELEMS * sizeof(T));
+    uint64_t* empty = full + G::STAGES;
+    unsigned bid = blockIdx.x;
+    const int cx = (int)(bid % ctas_x);
+    bid /= ctas_x;
+    const unsigned nbu = (unsigned)P.nb;
+    const int b = (int)(bid % nbu);
+    const int ny = P.g.ny, nx = P.g.nx;
+    const int band = HALO ? halo_band_order((int)(bid / nbu), (ny + ry - 1) / ry) : (int)(bid / nbu);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j0 = band * ry, j1 = j0 + ry < ny ? j0 + ry : ny;
+    const bool bottom = j0 == 0, top = j1 >= ny;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CGT_WARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (HALO) halo_wait<T>(P.halo, bottom, top);
+    const bool wrap = (P.g.flags & FL_WRAP_Y) != 0;
+    auto rowidx = [&](int r) { return wrap ? (r < 0 ? r + ny : (r >= ny ? r - ny : r)) : r; };
+    const int nstage = j1 - j0 + 2;  // rows j0-1 .. j1
+    if (warp == CGT_WARPS) {
+        // ---- producer warp: lane a owns array a (u, v, K0..K13, t2u, t2v, bar_u, bar_v) and issues that array's row
+        // copy itself, so a row of the ring is armed by one warp-wide cp.async.bulk instead of a 20-iteration loop of a
+        // single lane (measured: the single-lane producer took ~4000 cycles per row and starved the consumers)
+        const T* base = nullptr;
+        int64_t pitch = 0;
+        if (lane < 2) {
+            base = lane == 0 ? P.t1[0].p + (int64_t)b * P.t1[0].bstride : P.t1[1].p + (int64_t)b * P.t1[1].bstride;
+            pitch = P.t1[0].pitch;
+        }
+#pragma unroll
+        for (int k = 0; k < 14; ++k)
+            if (lane == 2 + k) {
+                base = plane_base<T>(P.plane[k], b);
+                pitch = P.plane[k].pitch;
+            }
+        if (NA == 20) {
+            if (lane == 16) { base = P.t2[0].p + (int64_t)b * P.t2[0].bstride; pitch = P.t2[0].pitch; }
+            if (lane == 17) { base = P.t2[1].p + (int64_t)b * P.t2[1].bstride; pitch = P.t2[1].pitch; }
+            if (lane == 18) { base = P.bar[0].p + (int64_t)b * P.bar[0].bstride; pitch = P.bar[0].pitch; }
+            if (lane == 19) { base = P.bar[1].p + (int64_t)b * P.bar[1].bstride; pitch = P.bar[1].pitch; }
+        }
+        if (HALO) asm volatile("fence.proxy.async;" ::: "memory");  // ghost rows written by the peer, acquired above
+        const int col0 = cx * CGT_COLS - G::HALO;
+        const int gx = col0 < 0 ? col0 + nx : col0;
+        const int n1 = (nx - gx) < G::LW ? (nx - gx) : G::LW;
+        for (int s = 0; s < nstage; ++s) {
+            const int slot = s % G::STAGES;
+            if (s >= G::STAGES) {
+                mbar_wait(&empty[slot], (unsigned)(((s / G::STAGES) - 1) & 1));
+                fence_proxy_async();
+            }
+            const int r = j0 - 1 + s;
+            const int na = (NA == 20 && r >= j0 && r < j1) ? 20 : 16;  // T_{i-2} / bar only exist for the owned rows
+            if (lane == 0) mbar_expect_tx(&full[slot], (unsigned)(na * G::LW * sizeof(T)));
+            __syncwarp();
+            if (lane < na) {
+                const T* row = base + (int64_t)rowidx(r) * pitch;
+                T* dst = ring + (size_t)slot * G::STAGE_ELEMS + lane * G::LW;
+                bulk_copy_g2s(dst, row + gx, (unsigned)(n1 * sizeof(T)), &full[slot]);
+                if (n1 < G::LW) bulk_copy_g2s(dst + n1, row, (unsigned)((G::LW - n1) * sizeof(T)), &full[slot]);
+            }
+        }
+    } else {  // ---- consumers: the marching recurrence of cgrid_march_kernel on shared-memory rows
+        const int lc = G::HALO - 1 + warp * CG_COLS + lane;
+        const int i = cx * CGT_COLS + warp * CG_COLS + lane - 1;
+        const bool emit_lane = lane >= 1 && lane <= CG_COLS && i < nx;
+        mbar_wait(&full[0], 0);
+        const T* s0 = ring + lc;
+        T u_j = s0[0], v_j = s0[G::LW];
+        T k0_j = s0[2 * G::LW], k1_j = s0[3 * G::LW], k2_j = s0[4 * G::LW], k3_j = s0[5 * G::LW];
+        T b_j, c_j, e_j, p1_j = T(0), p2_j = T(0), p3_jm = T(0);
+        {
+            const T zu = nan2num(u_j), zv = nan2num(v_j);
+            b_j = zv * k1_j; c_j = zv * k2_j; e_j = zu * k3_j;
+        }
+        for (int s = 0; s + 1 < nstage; ++s) {
+            const int j = j0 - 1 + s, sn = s + 1;
+            mbar_wait(&full[sn % G::STAGES], (unsigned)((sn / G::STAGES) & 1));
+            const T* cur = ring + (size_t)(s % G::STAGES) * G::STAGE_ELEMS + lc;
+            const T* nxt = ring + (size_t)(sn % G::STAGES) * G::STAGE_ELEMS + lc;
+            const T u_n = nxt[0], v_n = nxt[G::LW];
+            const T k0_n = nxt[2 * G::LW], k1_n = nxt[3 * G::LW], k2_n = nxt[4 * G::LW], k3_n = nxt[5 * G::LW];
+            const T k4 = nxt[6 * G::LW], k5 = nxt[7 * G::LW], k8 = nxt[10 * G::LW], k9 = nxt[11 * G::LW];
+            const T k6 = cur[8 * G::LW], k7 = cur[9 * G::LW], k10 = cur[12 * G::LW], k11 = cur[13 * G::LW];
+            const T zu = nan2num(u_n), zv = nan2num(v_n);
+            const T a_n = zu * k0_n, b_n = zv * k1_n, c_n = zv * k2_n, e_n = zu * k3_n;
+            const T a_w = __shfl_up_sync(0xffffffffu, a_n, 1);
+            const T sxx = -(k4 * (a_n - a_w) - k5 * (b_n - b_j));      // kernels.py:653-661
+            const T p1_n = k8 * sxx, p2_n = k9 * sxx;
+            const T c_e = __shfl_down_sync(0xffffffffu, c_j, 1);
+            const T sxy = -(k6 * (c_e - c_j) + k7 * (e_n - e_j));      // kernels.py:663-670
+            const T p3_j = k10 * sxy, p4_j = k11 * sxy;
+            const T p1_e = __shfl_down_sync(0xffffffffu, p1_j, 1);
+            const T p4_w = __shfl_up_sync(0xffffffffu, p4_j, 1);
+            if (j >= j0 && emit_lane) {  // kernels.py:672-694
+                T lap[2], x[2] = {u_j, v_j}, t2[2] = {T(0), T(0)}, bar[2] = {T(0), T(0)};
+                T uc = k0_j * (p1_j - p1_e);
+                uc = uc + k3_j * (p3_jm - p3_j);
+                lap[0] = uc * cur[14 * G::LW];
+                T vc = k2_j * (p4_w - p4_j);
+                vc = vc - k1_j * (p2_j - p2_n);
+                lap[1] = vc * cur[15 * G::LW];
+                if (NA == 20) {
+                    t2[0] = cur[16 * G::LW]; t2[1] = cur[17 * G::LW];
+                    bar[0] = cur[18 * G::LW]; bar[1] = cur[19 * G::LW];
+                }
+                cgt_tail<T, MODE, HALO>(P, b, j, i, lap, x, t2, bar);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s % G::STAGES]);  // this warp is done with row j's slot
+            u_j = u_n; v_j = v_n; b_j = b_n; c_j = c_n; e_j = e_n;
+            k0_j = k0_n; k1_j = k1_n; k2_j = k2_n; k3_j = k3_n;
+            p1_j = p1_n; p2_j = p2_n; p3_jm = p3_j;
+        }
+    }
+    if (HALO) halo_signal<T>(P.halo, bottom, top, ctas_x * nbu);
+}
+
 // Copy my first / last owned rows of a field into the neighbours' ghost rows and raise their flags (the
 // exchange of the prepared input before step 1).  One CTA column per x-block; grid (nxb, nb).
 template <typename T>
@@ -502,12 +685,65 @@ template <typename T, int MODE> static int launch_cgrid_march(const gcmf_plan* p
 }
 #endif
 
-template <typename T> static int launch_cgrid_mode(const gcmf_plan* pl, const StepParams<T>& P, int mode, cudaStream_t st) {
 #ifndef GCMF_HOSTEMU
-    // the marching kernel wraps column indices once: grids at least one warp wide; the tiled kernel covers the rest
-    // (and is the emulator's form of the operator: bit-identical, checked on the GPU by tests/cabi/gpu_vs_emu.c)
-    static const bool tiled = getenv("GCMF_CGRID_TILED") != nullptr;
-    if (!tiled && P.g.nx >= 32) {
+template <typename T, int MODE, bool HALO>
+static int launch_cgrid_tma_t(const gcmf_plan* pl, const StepParams<T>& P, cudaStream_t st) {
+    using G = CgtGeom<T>;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(cgrid_tma_kernel<T, MODE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)G::smem_bytes()));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    const int ctas_x = (P.g.nx + CGT_COLS - 1) / CGT_COLS;
+    // One CTA per SM (the ring takes most of the shared memory).  Rows per band, measured on cfg5 (ms per step): 17 rows
+    // 0.333, 34: 0.316, 68: 0.332, 135: 0.379, 270: 0.375 -- bands of ~34 rows (two priming rows = 6 %), shorter ones only
+    // when the launch would otherwise not fill the device.
+    int ry = 34;
+    {
+        const char* e = getenv("GCMF_CGRID_ROWS");
+        const int v = e ? atoi(e) : 0;
+        if (v > 0) {
+            ry = v;
+        } else {
+            const int64_t per_band = (int64_t)ctas_x * P.nb;
+            while (ry > 8 && per_band * ((P.g.ny + ry - 1) / ry) < pl->sm_count) ry = (ry + 1) / 2;
+        }
+    }
+    const int64_t nbands = (P.g.ny + ry - 1) / ry;
+    const int64_t nblk = (int64_t)ctas_x * P.nb * nbands;
+    if (nblk > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "grid too large (%lld blocks)", (long long)nblk);
+    cgrid_tma_kernel<T, MODE, HALO><<<(unsigned)nblk, 32 * (CGT_WARPS + 1), G::smem_bytes(), st>>>(P, (unsigned)ctas_x, ry);
+    gcmf_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCMF_OK;
+}
+template <typename T, int MODE> static int launch_cgrid_tma(const gcmf_plan* pl, const StepParams<T>& P, cudaStream_t st) {
+    if (P.halo.enabled) return launch_cgrid_tma_t<T, MODE, true>(pl, P, st);
+    return launch_cgrid_tma_t<T, MODE, false>(pl, P, st);
+}
+#endif
+
+// VECTOR_C dispatch.  aligned: every array of the launch is 16-byte aligned with vector-multiple strides (bulk copies).
+template <typename T>
+static int launch_cgrid_mode(const gcmf_plan* pl, const StepParams<T>& P, int mode, cudaStream_t st, bool aligned16) {
+#ifndef GCMF_HOSTEMU
+    // The tiled kernel covers grids narrower than a warp (and is the emulator's form of the operator: bit-identical,
+    // checked on the GPU by tests/cabi/gpu_vs_emu.c); GCMF_CGRID_KERNEL=tiled|march|tma forces one form (A/B, tests).
+    static const char* force = getenv("GCMF_CGRID_KERNEL");
+    const bool want_tiled = force && !strcmp(force, "tiled");
+    const bool want_march = force && !strcmp(force, "march");
+    if (!want_tiled && !want_march && aligned16 && P.g.nx >= CgtGeom<T>::LW) {
+        switch (mode) {
+            case MODE_LAP: return launch_cgrid_tma<T, MODE_LAP>(pl, P, st);
+            case MODE_FIRST: return launch_cgrid_tma<T, MODE_FIRST>(pl, P, st);
+            case MODE_MID: return launch_cgrid_tma<T, MODE_MID>(pl, P, st);
+            case MODE_LAST: return launch_cgrid_tma<T, MODE_LAST>(pl, P, st);
+        }
+    }
+    if (!want_tiled && P.g.nx >= 32) {  // the marching kernel wraps column indices once: grids at least one warp wide
         switch (mode) {
             case MODE_LAP: return launch_cgrid_march<T, MODE_LAP>(pl, P, st);
             case MODE_FIRST: return launch_cgrid_march<T, MODE_FIRST>(pl, P, st);
@@ -516,7 +752,7 @@ template <typename T> static int launch_cgrid_mode(const gcmf_plan* pl, const St
         }
     }
 #else
-    (void)pl;
+    (void)pl; (void)aligned16;
 #endif
     switch (mode) {
         case MODE_LAP: return launch_cgrid<T, MODE_LAP>(P, st);
@@ -554,7 +790,7 @@ static int launch_op(const gcmf_plan* pl, const StepParams<T>& P, int mode, cuda
             // tiled kernel needs every neighbour inside the array: at least 2 rows/columns; the point-wise
             // OpVectorC kernel remains for degenerate grids (and as the test oracle of the tiled one)
             static const bool pointwise = getenv("GCMF_CGRID_POINTWISE") != nullptr;
-            if (!pointwise && P.g.ny >= 2 && P.g.nx >= 2) return launch_cgrid_mode<T>(pl, P, mode, st);
+            if (!pointwise && P.g.ny >= 2 && P.g.nx >= 2) return launch_cgrid_mode<T>(pl, P, mode, st, VX > 1);
             return launch_mode<T, 1, OpVectorC<T, 1>>(P, mode, st);
         }
     }

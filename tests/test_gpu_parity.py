@@ -442,3 +442,63 @@ def test_operator_protocol_prepare_call_finalize():
     (f,), gv = fixtures.fixture("REGULAR_WITH_LAND", (48, 72))
     lap = ALL_KERNELS[GridType.REGULAR_WITH_LAND](**gv)
     assert lap.prepare(f) is f and lap.finalize(f) is f  # identity for the other operators (kernels.py:47-54)
+
+
+@pytest.mark.parametrize("g,shape", [("VECTOR_C_GRID", (96, 488)), ("VECTOR_C_GRID", (45, 100)), ("VECTOR_C_GRID", (40, 24)),
+                                     ("VECTOR_B_GRID", (64, 128)), ("IRREGULAR_WITH_LAND", (96, 264))])
+def test_peer_banded_single_rank_is_its_own_neighbour(g, shape):
+    """PeerBandedFilter with one rank (ordinary device memory, the band wraps onto itself): the step kernels' HALO forms
+    -- ghost rows pushed by the kernel, flag wait / signal, border bands scheduled first -- on one GPU, against the
+    whole-grid one-step kernels, bit for bit.  488 columns take the TMA-pipelined C-grid kernel, 100 the marching one,
+    24 the tiled one."""
+    from gcm_filters_b200 import engine
+    from gcm_filters_b200.scheduler import PeerBandedFilter
+    fields, gv = fixtures.fixture(g, shape)
+    fields = tuple(np.stack([f, 1.0 - f * f]) for f in fields)
+    fa = vec_args(g, gv, dict(filter_scale=6.0, dx_min=1.0))
+    flt = make_filter(g, gv, **fa)
+    try:
+        engine.set_steps_per_block(1)
+        single = run_filter(flt, fields)
+    finally:
+        engine.set_steps_per_block(0)
+    pbf = PeerBandedFilter(flt, 0, 1)
+    for _ in range(2):  # a second epoch on the reused buffers
+        outs, (j0, j1) = pbf.apply(*fields)
+    pbf.close()
+    assert (j0, j1) == (0, shape[0])
+    for o, s in zip(outs, single):
+        assert np.array_equal(o, s, equal_nan=True)
+
+
+@pytest.mark.parametrize("kernel", ["tiled", "march", "tma"])
+def test_cgrid_kernel_forms_are_bit_identical(kernel):
+    """The three device forms of the C-grid operator (tiled stress tiles, register marching, TMA-pipelined rows) run
+    the same expressions in the same order: identical bits, Laplacian and filter, odd and aligned widths."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, sys\n"
+        "from gcm_filters_b200 import Filter, GridType\n"
+        "from gcm_filters_b200.kernels import ALL_KERNELS\n"
+        "from oracle import fixtures\n"
+        "out = {}\n"
+        "for shape in ((70, 488), (37, 250), (33, 54)):\n"
+        "    (u, v), gv = fixtures.fixture('VECTOR_C_GRID', shape)\n"
+        "    lu, lv = ALL_KERNELS[GridType.VECTOR_C_GRID](**gv)(u, v)\n"
+        "    dxm = float(min(gv['dxT'].min(), gv['dyT'].min()))\n"
+        "    flt = Filter(filter_scale=5 * dxm, dx_min=dxm, grid_type=GridType.VECTOR_C_GRID, grid_vars=gv)\n"
+        "    fu, fv = flt.apply_to_vector(np.stack([u, v * u]), np.stack([v, u - v]), None)\n"
+        "    out[str(shape)] = np.stack([lu, lv]); out['f' + str(shape)] = np.stack([fu, fv])\n"
+        "np.savez(sys.argv[1], **out)\n")
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        res = {}
+        for k in ("tiled", kernel):
+            path = os.path.join(tmp, k + ".npz")
+            env = dict(os.environ, GCMF_CGRID_KERNEL=k, PYTHONPATH=os.pathsep.join(sys.path))
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+            res[k] = dict(np.load(path))
+        for key in res["tiled"]:
+            assert np.array_equal(res["tiled"][key], res[kernel][key], equal_nan=True), (kernel, key)
