@@ -42,10 +42,11 @@ DATA = "synthetic (numpy PCG64, SURVEY 8(d))"
 # ------------------------------------------------------------------------------------------ workloads
 def workload_nb(name, nb):
     """Batch size (levels / time steps) of the whole field of a workload; None = a single 2-D field."""
-    default = {"cfg3": 62, "cfg3f32": 62, "cfg3taper": 62, "cfg2": 365, "cfg4": None, "cfg5": None, "cfg1": None}
+    default = {"cfg3": 62, "cfg3f32": 62, "cfg3taper": 62, "cfg2": 365, "cfg4": None, "cfg5": None, "cfg1": None,
+               "cfgb": None}
     if name not in default:
         raise SystemExit(f"unknown workload {name}")
-    if name in ("cfg5", "cfg1"):
+    if name in ("cfg5", "cfg1", "cfgb"):
         return None
     return nb or default[name]
 
@@ -68,6 +69,8 @@ def build_workload(name, nb=0, levels=None):
         return fixtures.cfg4(nb=nbt, levels=levels if nbt else None)
     if name == "cfg5":
         return fixtures.cfg5()
+    if name == "cfgb":
+        return fixtures.cfgb()
     return fixtures.cfg1()
 
 

@@ -170,3 +170,12 @@ def cfg5(shape=(2160, 4320)):
     dx_min = float(min(gv["dxT"][wet].min(), gv["dyT"][wet].min()))
     return dict(name="cfg5", grid_type="VECTOR_C_GRID", fields=(u, v), grid_vars=gv,
                 filter_args=dict(filter_scale=20.0 * dx_min, dx_min=dx_min, filter_shape="GAUSSIAN"))
+
+
+def cfgb(shape=(2160, 4320)):
+    """VECTOR_B_GRID (POP B-grid viscosity operator) on the cfg5 geometry, fp64 -- not a BASELINE config; used to
+    profile the one-step kernel of the fourth operator family."""
+    (u, v), gv = vector_fixture("VECTOR_B_GRID", shape)
+    dx_min = float(min(gv["DXU"].min(), gv["DYU"].min()))
+    return dict(name="cfgb", grid_type="VECTOR_B_GRID", fields=(u, v), grid_vars=gv,
+                filter_args=dict(filter_scale=20.0 * dx_min, dx_min=dx_min, filter_shape="GAUSSIAN"))

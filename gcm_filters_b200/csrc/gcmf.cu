@@ -27,6 +27,9 @@
 #include "gcmf_internal.h"
 #include "gcmf_stencils.cuh"
 #include "gcmf_fused.cuh"
+#ifndef GCMF_HOSTEMU
+#include "gcmf_march.cuh"
+#endif
 
 using namespace gcmf;
 
@@ -1240,6 +1243,68 @@ static int launch_fused_kernel(gcmf_plan* pl, const FusedParams<T>& P, int64_t n
 }
 #endif
 
+#ifndef GCMF_HOSTEMU
+// ---- row-streaming form of the fused FLUX steps (gcmf_march.cuh) ----------------------------------------------
+// Eligible: FLUX family, no tripolar fold / cut (periodic whole grids and latitude bands), every array 16-byte aligned
+// (checked by the caller), grid at least one strip wide.  GCMF_FUSED_FORM=tile|march forces one form (A/B, tests).
+static bool march_eligible(const gcmf_plan* pl) {
+    static const char* force = getenv("GCMF_FUSED_FORM");
+    if (force && !strcmp(force, "tile")) return false;
+    if (pl->desc.op != GCMF_OP_FLUX) return false;
+    if (pl->desc.flags & (GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S)) return false;
+    return pl->desc.nx >= MARCH_W;
+}
+
+template <typename T, int EDGE, int K> static int launch_march_t(const gcmf_plan* pl, const FusedParams<T>& P, cudaStream_t st) {
+    using G = MarchGeom<T>;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(march_kernel<T, EDGE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)G::smem_bytes()));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    const int nstrips = (P.g.nx + G::SW - 1) / G::SW;
+    const int nlg = (int)((P.nb + MARCH_LV - 1) / MARCH_LV);
+    // rows per band: 2(K-1) priming iterations per band against enough CTAs to fill the device several times over
+    int ry = 120;
+    {
+        const char* e = getenv("GCMF_MARCH_ROWS");
+        const int v = e ? atoi(e) : 0;
+        if (v > 0) {
+            ry = v;
+        } else {
+            const int64_t per_band = (int64_t)nstrips * nlg;
+            while (ry > 24 && per_band * ((P.g.ny + ry - 1) / ry) < 4 * (int64_t)pl->sm_count) ry = (ry + 1) / 2;
+        }
+    }
+    const int64_t nbands = (P.g.ny + ry - 1) / ry;
+    const int64_t ncta = (int64_t)nstrips * nlg * nbands;
+    if (ncta > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "fused step: grid too large");
+    march_kernel<T, EDGE, K><<<(unsigned)ncta, G::NTHREADS, G::smem_bytes(), st>>>(P, nstrips, nlg, ry);
+    gcmf_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCMF_OK;
+}
+template <typename T, int EDGE> static int launch_march_e(const gcmf_plan* pl, const FusedParams<T>& P, cudaStream_t st) {
+    switch (P.k) {
+        case 1: return launch_march_t<T, EDGE, 1>(pl, P, st);
+        case 2: return launch_march_t<T, EDGE, 2>(pl, P, st);
+        case 3: return launch_march_t<T, EDGE, 3>(pl, P, st);
+    }
+    return launch_march_t<T, EDGE, 4>(pl, P, st);
+}
+template <typename T> static int launch_march(const gcmf_plan* pl, const FusedParams<T>& P, cudaStream_t st) {
+    switch ((P.first ? 1 : 0) | (P.last ? 2 : 0)) {
+        case 0: return launch_march_e<T, 0>(pl, P, st);
+        case 1: return launch_march_e<T, 1>(pl, P, st);
+        case 2: return launch_march_e<T, 2>(pl, P, st);
+    }
+    return launch_march_e<T, 3>(pl, P, st);
+}
+#endif
+
 template <typename T>
 static int run_fused_t(gcmf_plan* pl, int64_t nb, int step0, int k, const gcmf_field* t1, const gcmf_field* t2,
                        const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st) {
@@ -1307,6 +1372,7 @@ static int run_fused_t(gcmf_plan* pl, int64_t nb, int step0, int k, const gcmf_f
     gcmf_count_launch(1);
     return GCMF_OK;
 #else
+    if (kind == FK_FLUX && march_eligible(pl)) return launch_march<T>(pl, P, st);
     if (kind == FK_FLUX) return launch_fused_kernel<T, FK_FLUX>(pl, P, ncta, st);
     return launch_fused_kernel<T, FK_REG5>(pl, P, ncta, st);
 #endif

@@ -145,6 +145,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, unsigned parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(mb)), "r"(parity) : "memory");
 }
+// non-blocking probe of a phase
+__device__ __forceinline__ unsigned mbar_test(uint64_t* mb, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(mb)), "r"(parity) : "memory");
+    return ok;
+}
 // ---- drain counter of the landing tiles (acquire-release at CTA scope) ----
 __device__ __forceinline__ uint32_t atom_add_acqrel_u32(uint32_t* p, uint32_t v) {
     uint32_t old;
