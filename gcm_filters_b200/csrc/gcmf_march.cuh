@@ -7,23 +7,25 @@
 //
 //   * a CTA owns a strip of 120 output columns (+ 4 halo columns per side = 128 threads) of MARCH_LV levels at once
 //     and marches north through a band of rows, one row per iteration;
-//   * the k steps run as a software pipeline along the march: in iteration t a thread (one column of one level)
-//     performs step 1 at row t, step 2 at row t-1, ... step k at row t-k+1 -- each step's north neighbour is the
-//     value the previous step of the same iteration has just produced, its own and south values are two registers
-//     per stage, so N / S neighbours never touch shared memory and there is NO redundant row work inside a band
-//     (the tile form recomputes 4 halo rows per 24);
-//   * only the W / E neighbours go through shared memory: every thread publishes the k values it produced (sanitized)
-//     in a double-buffered exchange row and reads its two neighbours' in the next iteration -- one named barrier per
-//     iteration and level (128 threads);
-//   * rows of T_{i-1}, T_{i-2}, bar of the LV levels and of the three coefficient planes (shared by the levels) are
-//     streamed through a 10-slot shared-memory ring (one lane per array, cp.async.bulk -> UBLKCP, mbarrier
-//     complete_tx), up to four rows ahead; consumers release a row k iterations after they first used it.  Warp 0
-//     doubles as the producer at the top of its iterations: a 17th warp would cap every thread at 96 registers (the
-//     register file is split over four sub-partitions: 5 warps on one of them), which spills.
+//   * the K steps run as a software pipeline along the march, two rows apart: in iteration t a thread (one column of
+//     one level) performs step 1 at row t, step 2 at row t-2, ... step K at row t-2(K-1).  Every input of every step
+//     was produced in an earlier iteration, so the K steps of an iteration are INDEPENDENT (a first version with the
+//     steps one row apart fed each step's result to the next one as its north neighbour: four dependent fp64 chains per
+//     iteration, 1.3x slower than the tile form).  The N / S neighbours of a point are registers of the same thread
+//     (three rows per stage), there is NO redundant row work inside a band (the tile form recomputes 4 halo rows per 24);
+//   * only the W / E neighbours go through shared memory: at the top of an iteration every thread publishes the K
+//     values that become stage centres in the next iteration (sanitized) in a double-buffered exchange row -- one named
+//     barrier per iteration and level (128 threads);
+//   * rows of T_{i-1}, T_{i-2}, bar of the LV levels (8-slot ring) and of the three coefficient planes, shared by the
+//     levels (16-slot ring: a coefficient row stays in use for 2K iterations), are streamed by the TMA engine (one lane
+//     per array, cp.async.bulk -> UBLKCP, mbarrier complete_tx) several rows ahead by a dedicated producer warp.
+//     (MARCH_LV = 3: with four levels the producer would be a 17th warp, five warps on one of the four register-file
+//     sub-partitions, which caps every thread at 96 registers and spills; folding the producer duty into consumer
+//     warp 0 instead made the whole CTA run at that warp's pace -- measured 1.3x to 2x slower than the tile form.)
 //
-// HBM traffic per grid-point step: (6w + 3w/LV) / k * (128/120) = 14.4 B (fp64, k = 4) plus 2(k-1) priming rows per
-// band, against 13.1 B of the tile form -- but all 16 warps do the same work, the per-step shared-memory traffic is
-// 6 LDS.64 + 1 STS.64 per point instead of a full tile sweep, and the per-thread state is 2 rows x k stages.
+// HBM traffic per grid-point step: (6w + 3w/LV) / K * (128/120) = 14.4 B (fp64, K = 4) plus 3(K-1) priming iterations
+// per band, against 13.1 B of the tile form -- but all 16 warps do the same work, the per-step shared-memory traffic is
+// 7 LDS.64 + 1 STS.64 per point instead of a full tile sweep.
 //
 // The arithmetic of a point is the same inline code as everywhere else (flux_lap, shifted_flux, cheb_next,
 // bar_update): results are bit-identical to the tile form and to the one-step kernels.
@@ -34,22 +36,25 @@
 namespace gcmf {
 
 #ifndef GCMF_MARCH_LV
-#define GCMF_MARCH_LV 4
+#define GCMF_MARCH_LV 3  // 12 consumer warps + the producer warp = 13 warps: at most 4 on a sub-partition, 128 registers
 #endif
 constexpr int MARCH_LV = GCMF_MARCH_LV;  // levels per CTA (they share the coefficient rows)
 constexpr int MARCH_W = 128;             // threads per level = staged columns per row
-constexpr int MARCH_D = 10;              // ring slots (rows)
+constexpr int MARCH_DS = 8;              // state ring slots (rows of T1, T2, bar of every level)
+constexpr int MARCH_DC = 16;             // coefficient ring slots (rows of ce, cn, ra)
 
 template <typename T> struct MarchGeom {
     static constexpr int H = FUSED_H;
     static constexpr int SW = MARCH_W - 2 * H;                   // output columns per strip: 120
-    static constexpr int NARR = 3 * MARCH_LV + 3;                // T1, T2, bar per level + ce, cn, ra
-    static constexpr int SLOT = NARR * MARCH_W;                  // elements per ring slot
+    static constexpr int NS = 3 * MARCH_LV;                      // state arrays of a row: T1, T2, bar per level
+    static constexpr int SSLOT = NS * MARCH_W;                   // elements per state slot
+    static constexpr int CSLOT = 3 * MARCH_W;                    // elements per coefficient slot
     static constexpr int XB = 2 * MARCH_LV * FUSED_H * MARCH_W;  // exchange rows: [parity][level][stage][column]
     static constexpr int PAD = 16;                               // elements in front of the exchange rows (column -1 reads)
-    static constexpr int NTHREADS = MARCH_W * MARCH_LV;
+    static constexpr int NTHREADS = MARCH_W * MARCH_LV + 32;
+    static constexpr int NBAR = 2 * (MARCH_DS + MARCH_DC);
     static constexpr size_t smem_bytes() {
-        return ((size_t)PAD + XB + (size_t)MARCH_D * SLOT) * sizeof(T) + 2 * MARCH_D * sizeof(uint64_t) + 128;
+        return ((size_t)PAD + XB + (size_t)MARCH_DC * CSLOT + (size_t)MARCH_DS * SSLOT + PAD) * sizeof(T) + NBAR * sizeof(uint64_t) + 128;
     }
 };
 
@@ -66,14 +71,17 @@ __global__ void __launch_bounds__(MarchGeom<T>::NTHREADS, 1)
     using G = MarchGeom<T>;
     constexpr bool FIRST = (EDGE & 1) != 0, LAST = (EDGE & 2) != 0;
     constexpr int H = G::H;
-    // shared memory: [pad][exchange rows][ring][barriers].  West / east neighbours are read at column +-1 without
-    // clamping: column -1 of the first array / +1 of the last one fall into the pad, the neighbouring array or the
-    // barrier words -- defined memory whose value only reaches cells outside the dependency cone.
+    // shared memory: [pad][exchange rows][coefficient ring][state ring][pad][barriers].  West / east neighbours are read
+    // at column +-1 without clamping: column -1 of the first array / +1 of the last one fall into a pad or the
+    // neighbouring array -- defined memory whose value only reaches cells outside the dependency cone.
     extern __shared__ __align__(128) unsigned char march_smem[];
     T* xb = reinterpret_cast<T*>(march_smem) + G::PAD;
-    T* ring = xb + G::XB;
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)MARCH_D * G::SLOT);
-    uint64_t* empty = full + MARCH_D;
+    T* cring = xb + G::XB;
+    T* sring = cring + (size_t)MARCH_DC * G::CSLOT;
+    uint64_t* fullS = reinterpret_cast<uint64_t*>(sring + (size_t)MARCH_DS * G::SSLOT + G::PAD);
+    uint64_t* emptyS = fullS + MARCH_DS;
+    uint64_t* fullC = emptyS + MARCH_DS;
+    uint64_t* emptyC = fullC + MARCH_DC;
 
     // block id -> (level group fastest: the groups of one strip / band re-read the same coefficient rows, strip, band)
     unsigned bid = blockIdx.x;
@@ -90,40 +98,22 @@ __global__ void __launch_bounds__(MarchGeom<T>::NTHREADS, 1)
     // row r of the arrays: periodic, or a latitude band with FUSED_H ghost rows physically present on either side
     auto rowidx = [&](int r) { return wrap ? (r < 0 ? r + ny : (r >= ny ? r - ny : r)) : r; };
     const int R0 = j0 - K;                 // first staged row
-    const int nrows = (j1 - j0) + 2 * K;   // staged rows R0 .. j1 + K - 1
+    const int nrows = (j1 - j0) + 2 * K;   // staged rows R0 .. j1 + K - 1 (both rings)
     if (tid == 0) {
-        for (int s = 0; s < MARCH_D; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], (unsigned)(nlev * (MARCH_W / 32)));
-        }
+        const unsigned nw = (unsigned)(nlev * (MARCH_W / 32));
+        for (int s = 0; s < MARCH_DS; ++s) { mbar_init(&fullS[s], 1); mbar_init(&emptyS[s], nw); }
+        for (int s = 0; s < MARCH_DC; ++s) { mbar_init(&fullC[s], 1); mbar_init(&emptyC[s], nw); }
         fence_mbar_init();
     }
     __syncthreads();
 
-    // ---- thread = (level l, column c)
-    const int l = tid / MARCH_W, c = tid % MARCH_W;
-    if (l >= nlev) return;
-    const int64_t lev = lev0 + l;
-    const int gc = cx * G::SW + c - H;  // global column (unwrapped)
-    const bool emit_col = c >= H && c < MARCH_W - H && gc < nx;
-    const T cc = (T)P.c;
-    // element offsets of the arrays inside a slot, relative to this thread's column of array 0
-    const int oT1 = 3 * l * MARCH_W, oT2 = oT1 + MARCH_W, oBar = oT2 + MARCH_W;
-    constexpr int oCe = 3 * MARCH_LV * MARCH_W, oCn = oCe + MARCH_W, oRa = oCn + MARCH_W;
-    const T* const ring_c = ring + c;
-    const T* const ring_end = ring_c + (size_t)MARCH_D * G::SLOT;
-    constexpr int XBP = MARCH_LV * FUSED_H * MARCH_W;
-    T* xr = xb + (size_t)l * FUSED_H * MARCH_W + c;  // exchange rows read in this iteration ...
-    T* xw = xr + XBP;                                // ... and written for the next one
-
-    // ---- producer duty of warp 0: lane a owns array a of a slot (level-major T1, T2, bar; then ce, cn, ra)
-    const bool producer = tid < 32;
-    const T* pbase = nullptr;
-    int64_t ppitch = 0;
-    bool pbar = false;
-    if (producer) {
-        const int lane = tid;
-        if (lane < 3 * MARCH_LV) {
+    if (tid >= MARCH_W * MARCH_LV) {
+        // ---- producer warp: lanes 0..NS-1 own the state arrays (level-major T1, T2, bar), NS..NS+2 own ce, cn, ra
+        const int lane = tid & 31;
+        const T* pbase = nullptr;
+        int64_t ppitch = 0;
+        bool pbar = false;
+        if (lane < G::NS) {
             const int pl_ = lane / 3, kind = lane % 3;
             if (pl_ < nlev) {
                 const int64_t plev = lev0 + pl_;
@@ -131,163 +121,168 @@ __global__ void __launch_bounds__(MarchGeom<T>::NTHREADS, 1)
                 if (kind == 1 && !FIRST) { pbase = P.t2_in.p + plev * P.t2_in.bstride; ppitch = P.t2_in.pitch; }
                 if (kind == 2 && !FIRST) { pbase = P.bar.p + plev * P.bar.bstride; ppitch = P.bar.pitch; pbar = true; }
             }
-        } else if (lane < G::NARR) {
-            const int pc = lane - 3 * MARCH_LV;
+        } else if (lane < G::NS + 3) {
+            const int pc = lane - G::NS;
             pbase = reinterpret_cast<const T*>(pc == 0 ? P.plane[0].p : (pc == 1 ? P.plane[1].p : P.plane[2].p));
             ppitch = pc == 0 ? P.plane[0].pitch : (pc == 1 ? P.plane[1].pitch : P.plane[2].pitch);
         }
-    }
-    const int pcol0 = cx * G::SW - H;
-    const int pgx = pcol0 < 0 ? pcol0 + nx : pcol0;
-    const int pn1 = (nx - pgx) < MARCH_W ? (nx - pgx) : MARCH_W;
-    const unsigned per = (unsigned)(MARCH_W * sizeof(T));
-    const unsigned tx_halo = per * (unsigned)(3 + nlev * (FIRST ? 1 : 2));  // bar only exists for the owned rows
-    const unsigned tx_own = per * (unsigned)(3 + nlev * (FIRST ? 1 : 3));
-    int next_s = 0;  // next row of the band to stage (producer warp)
-    // stage rows up to `upto`; rows up to `must` are waited for (they are needed next), later ones only if their slot is free
-    auto produce = [&](int upto, int must) {
-        while (next_s < nrows && R0 + next_s <= upto) {
-            const int slot = next_s % MARCH_D;
-            if (next_s >= MARCH_D) {
-                const unsigned par = (unsigned)(((next_s / MARCH_D) - 1) & 1);
-                if (R0 + next_s <= must) {
-                    mbar_wait(&empty[slot], par);
-                } else {
-                    unsigned ok = 0;
-                    if (tid == 0) ok = mbar_test(&empty[slot], par);
-                    ok = __shfl_sync(0xffffffffu, ok, 0);
-                    if (!ok) break;
-                }
-                fence_proxy_async();
-            }
-            const int r = R0 + next_s;
+        const int pcol0 = cx * G::SW - H;
+        const int pgx = pcol0 < 0 ? pcol0 + nx : pcol0;
+        const int pn1 = (nx - pgx) < MARCH_W ? (nx - pgx) : MARCH_W;
+        const unsigned per = (unsigned)(MARCH_W * sizeof(T));
+        const unsigned tx_halo = per * (unsigned)(nlev * (FIRST ? 1 : 2));  // bar only exists for the owned rows
+        const unsigned tx_own = per * (unsigned)(nlev * (FIRST ? 1 : 3));
+        T* const dstS = sring + lane * MARCH_W;
+        T* const dstC = cring + (lane - G::NS) * MARCH_W;
+        for (int i = 0; i < nrows; ++i) {  // one row of either ring per iteration, as soon as its slot is free
+            const int r = R0 + i;
             const bool own = r >= j0 && r < j1;
-            if (tid == 0) mbar_expect_tx(&full[slot], own ? tx_own : tx_halo);
+            const int ss = i & (MARCH_DS - 1), sc = i & (MARCH_DC - 1);
+            if (i >= MARCH_DS) mbar_wait(&emptyS[ss], (unsigned)(((i / MARCH_DS) - 1) & 1));
+            if (i >= MARCH_DC) mbar_wait(&emptyC[sc], (unsigned)(((i / MARCH_DC) - 1) & 1));
+            if (i >= MARCH_DS) fence_proxy_async();
+            if (lane == 0) {
+                mbar_expect_tx(&fullS[ss], own ? tx_own : tx_halo);
+                mbar_expect_tx(&fullC[sc], 3u * per);
+            }
             __syncwarp();
             if (pbase != nullptr && (!pbar || own)) {
                 const T* row = pbase + (int64_t)rowidx(r) * ppitch;
-                T* dst = ring + (size_t)slot * G::SLOT + tid * MARCH_W;
-                bulk_copy_g2s(dst, row + pgx, (unsigned)(pn1 * sizeof(T)), &full[slot]);
-                if (pn1 < MARCH_W) bulk_copy_g2s(dst + pn1, row, (unsigned)((MARCH_W - pn1) * sizeof(T)), &full[slot]);
+                const bool state = lane < G::NS;
+                T* dst = state ? dstS + (size_t)ss * G::SSLOT : dstC + (size_t)sc * G::CSLOT;
+                uint64_t* fb = state ? &fullS[ss] : &fullC[sc];
+                bulk_copy_g2s(dst, row + pgx, (unsigned)(pn1 * sizeof(T)), fb);
+                if (pn1 < MARCH_W) bulk_copy_g2s(dst + pn1, row, (unsigned)((MARCH_W - pn1) * sizeof(T)), fb);
             }
-            ++next_s;
         }
-    };
+        return;
+    }
 
-    // per-stage state: stage s = input of step s+1; S / C = rows (t-s-1, t-s) at the start of iteration t
-    T sanS[K], sanC[K], rawS[K], rawC[K], acc[K];
+    // ---- consumers: thread = (level l, column c)
+    const int l = tid / MARCH_W, c = tid % MARCH_W;
+    if (l >= nlev) return;
+    const int64_t lev = lev0 + l;
+    const int gc = cx * G::SW + c - H;  // global column (unwrapped)
+    const bool emit_col = c >= H && c < MARCH_W - H && gc < nx;
+    const T cc = (T)P.c;
+    const int oT1 = 3 * l * MARCH_W, oT2 = oT1 + MARCH_W, oBar = oT2 + MARCH_W;  // arrays inside a state slot
+    constexpr int oCe = 0, oCn = MARCH_W, oRa = 2 * MARCH_W;                      // arrays inside a coefficient slot
+    const T* const sring_c = sring + c;
+    const T* const cring_c = cring + c;
+    // ring row of staged index idx (= row - R0)
+    auto srow = [&](int idx) { return sring_c + (size_t)(idx & (MARCH_DS - 1)) * G::SSLOT; };
+    auto crow = [&](int idx) { return cring_c + (size_t)(idx & (MARCH_DC - 1)) * G::CSLOT; };
+    constexpr int XBP = MARCH_LV * FUSED_H * MARCH_W;
+    T* xr = xb + (size_t)l * FUSED_H * MARCH_W + c;  // exchange rows read in this iteration ...
+    T* xw = xr + XBP;                                // ... and written for the next one
+    auto wait_full = [&](uint64_t* fullb, int D, int idx) { mbar_wait(&fullb[idx & (D - 1)], (unsigned)((idx / D) & 1)); };
+
+    // ---- per-thread pipeline state.  Stage q (0..K-1) is the input of step q+1, which runs at row t-2q in iteration t:
+    //   san{S,C,N}[q]  sanitized stage-q values at rows t-2q-1, t-2q, t-2q+1
+    //   raw{SS,S,C,N}[q]  raw values at rows t-2q-2 .. t-2q+1 (C: the "-x" term of step q+1; SS: T_{i-2} of step q+2)
+    //   accA / accB[q]  running bar of the rows that finished step q+1 one / two iterations ago
+    T sanS[K], sanC[K], sanN[K], rawSS[K], rawS[K], rawC[K], rawN[K], accA[K], accB[K];
 #pragma unroll
-    for (int s = 0; s < K; ++s) sanS[s] = sanC[s] = rawS[s] = rawC[s] = acc[s] = T(0);
-    const int t0 = j0 - (K - 1), t1 = j1 - 1 + (K - 1);
-    if (producer) produce(R0 + MARCH_D - 1, R0 + MARCH_D - 1);  // fill the ring
-    // ring rows in use in iteration t: row[i] = this thread's column of array 0 of row t+1-i, i = 0 .. K+1
-    const T* row[K + 2];
-    // staged index of row t0-1 is 0 (t0 - 1 = R0), of row t0 is 1: the loop starts with row t0+1 = index 2
-    int fslot = 2 % MARCH_D;   // slot of the row waited for in the next iteration
-    unsigned fpar = 0;
-    int eslot = 0;             // slot released next (row t - K)
-    {   // prologue: rows t0-1 and t0 of the input
-        mbar_wait(&full[0], 0);
-        mbar_wait(&full[1], 0);
-        // state "at the end of iteration t0-1": row[0] = row t0 (slot 1), row[1] = row t0-1 (slot 0); the rows below R0
-        // do not exist and are never dereferenced (their steps are inactive)
-#pragma unroll
-        for (int i = 0; i < K + 2; ++i) row[i] = ring_c;
-        row[0] = ring_c + G::SLOT;
-        rawS[0] = ring_c[oT1];
-        rawC[0] = ring_c[G::SLOT + oT1];
+    for (int q = 0; q < K; ++q)
+        sanS[q] = sanC[q] = sanN[q] = rawSS[q] = rawS[q] = rawC[q] = rawN[q] = accA[q] = accB[q] = T(0);
+    const int t0 = j0 - (K - 1), t1 = j1 - 1 + 2 * (K - 1);
+    const int last_idx = nrows - 1;
+    {   // prologue: stage 0 holds rows t0-1, t0, t0+1 (staged indices 0, 1, 2); coefficient rows 0 and 1
+        wait_full(fullS, MARCH_DS, 0);
+        wait_full(fullS, MARCH_DS, 1);
+        wait_full(fullS, MARCH_DS, 2);
+        wait_full(fullC, MARCH_DC, 0);
+        rawS[0] = srow(0)[oT1];
+        rawC[0] = srow(1)[oT1];
+        rawN[0] = srow(2)[oT1];
         sanS[0] = nan2num(rawS[0]);
         sanC[0] = nan2num(rawC[0]);
-        xr[0] = sanC[0];
+        sanN[0] = nan2num(rawN[0]);
+        xr[0] = sanC[0];  // what the neighbours read as stage-0 centre in the first iteration
 #pragma unroll
-        for (int s = 1; s < FUSED_H; ++s) xr[s * MARCH_W] = T(0);
+        for (int q = 1; q < FUSED_H; ++q) xr[q * MARCH_W] = T(0);
+        // state row 0 (row t0-1) only contributes its T1, lifted just now: release its slot (the loop releases row t in
+        // iteration t, starting with staged index 1)
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&emptyS[0]);
         named_barrier(1 + l, MARCH_W);
     }
-    // running element offsets of the output rows (row rk = t - (K-1))
-    int64_t ob = lev * P.bar.bstride + (int64_t)(t0 - (K - 1)) * P.bar.pitch + gc;
+    // running element offsets of the output rows (row rk = t - 2(K-1))
+    int64_t ob = lev * P.bar.bstride + (int64_t)(t0 - 2 * (K - 1)) * P.bar.pitch + gc;
     int64_t o1 = 0, o2 = 0;
     if (!LAST) {
-        o1 = lev * P.t1_out.bstride + (int64_t)(t0 - (K - 1)) * P.t1_out.pitch + gc;
-        o2 = lev * P.t2_out.bstride + (int64_t)(t0 - (K - 1)) * P.t2_out.pitch + gc;
+        o1 = lev * P.t1_out.bstride + (int64_t)(t0 - 2 * (K - 1)) * P.t1_out.pitch + gc;
+        o2 = lev * P.t2_out.bstride + (int64_t)(t0 - 2 * (K - 1)) * P.t2_out.pitch + gc;
     }
 #pragma unroll 1
     for (int t = t0; t <= t1; ++t) {
-        if (producer) produce(t + 1 + MARCH_D, t + 2);  // as far ahead as released slots allow; row t+2 at the latest
-        // rotate the row pointers: row[0] becomes row t+1
+        const int ti = t - R0;  // staged index of row t
+        // publish what becomes the stage centres of the next iteration: the north rows held now
 #pragma unroll
-        for (int i = K + 1; i > 0; --i) row[i] = row[i - 1];
-        {
-            const T* nx_ = row[1] + G::SLOT;
-            row[0] = nx_ == ring_end ? ring_c : nx_;
+        for (int q = 0; q < K; ++q) xw[q * MARCH_W] = sanN[q];
+        // new north row of stage 0 for the next iteration: input row t+2
+        T rawN0 = T(0);
+        if (ti + 2 <= last_idx) {
+            wait_full(fullS, MARCH_DS, ti + 2);
+            rawN0 = srow(ti + 2)[oT1];
         }
-        mbar_wait(&full[fslot], fpar);
-        if (++fslot == MARCH_D) { fslot = 0; fpar ^= 1u; }
-        const T rawN0 = row[0][oT1];
-        const T sanN0 = nan2num(rawN0);
-        xw[0] = sanN0;
+        if (ti <= last_idx) wait_full(fullC, MARCH_DC, ti);
         T t2in = T(0), barin = T(0);
-        if (!FIRST) {
-            t2in = row[1][oT2];
-            if (t >= j0 && t < j1) barin = row[1][oBar];
+        if (!FIRST && ti <= last_idx) {
+            t2in = srow(ti)[oT2];
+            if (t >= j0 && t < j1) barin = srow(ti)[oBar];
         }
-        T on = sanN0, rawN = rawN0;  // north input of the current step = the value entering stage s-1 in this iteration
-        T newsan[K], newraw[K], newacc[K];
+        T tn[K], an[K];
 #pragma unroll
         for (int s = 1; s <= K; ++s) {
-            const int r = t - (s - 1);
-            newraw[s - 1] = rawN;   // becomes the centre of stage s-1 in the next iteration
-            newsan[s - 1] = on;
-            // step s at row r feeds an owned row only inside the dependency cone of the band (uniform over the CTA);
-            // outside it nothing is computed and nothing staged is touched (rows below R0 + 1 do not exist in the ring)
+            const int q = s - 1;
+            const int r = t - 2 * q;
+            // step s at row r feeds an owned row only inside the dependency cone of the band (uniform over the CTA)
             const bool active = r >= j0 - (K - s) && r <= j1 - 1 + (K - s);
-            T tn = T(0);
-            newacc[s - 1] = T(0);
+            tn[q] = T(0);
+            an[q] = T(0);
             if (active) {
-                const T* cr = row[s];        // ring row r
-                const T* crs = row[s + 1];   // ring row r-1: its north faces are the south faces of row r
-                const T lap = flux_lap<T>(sanC[s - 1], xr[(s - 1) * MARCH_W - 1], xr[(s - 1) * MARCH_W + 1], on, sanS[s - 1],
+                const T* cr = crow(ti - 2 * q);       // coefficient row r
+                const T* crs = crow(ti - 2 * q - 1);  // row r-1: its north faces are the south faces of row r
+                const T lap = flux_lap<T>(sanC[q], xr[q * MARCH_W - 1], xr[q * MARCH_W + 1], sanN[q], sanS[q],
                                           cr[oCe], cr[oCe - 1], cr[oCn], crs[oCn], cr[oRa]);
-                const T a = shifted_flux<T>(rawC[s - 1], cc, lap);                       // filter.py:171
+                const T a = shifted_flux<T>(rawC[q], cc, lap);                           // filter.py:171
                 const bool start = FIRST && s == 1;
-                const T tm2 = s == 1 ? t2in : rawS[s >= 2 ? s - 2 : 0];
-                tn = start ? a : cheb_next<T>(a, tm2);                                    // filter.py:192-194 / 197-203
-                // acc of row r after step s-1 = what step s-1 left in the previous iteration
-                const double b0 = s == 1 ? (start ? P.p0 * (double)rawC[0] : (double)barin) : (double)acc[s >= 2 ? s - 2 : 0];
-                newacc[s - 1] = (T)bar_update(b0, P.p[s - 1], (double)tn);               // filter.py:195 / 204
-            }
-            // the value just produced is the north input of the next step (one row further south)
-            rawN = tn;
-            if (s < K) {
-                on = nan2num(tn);
-                if (active) xw[s * MARCH_W] = on;
+                const T tm2 = s == 1 ? t2in : rawSS[q >= 1 ? q - 1 : 0];
+                tn[q] = start ? a : cheb_next<T>(a, tm2);                                 // filter.py:192-194 / 197-203
+                const double b0 = s == 1 ? (start ? P.p0 * (double)rawC[0] : (double)barin) : (double)accB[q >= 1 ? q - 1 : 0];
+                an[q] = (T)bar_update(b0, P.p[q], (double)tn[q]);                        // filter.py:195 / 204
             }
         }
-        // outputs of row rk = t-(K-1): T_{i+K-1} = the last value produced, T_{i+K-2} = centre of stage K-1
-        const int rk = t - (K - 1);
+        // outputs of row rk = t-2(K-1): T_{i+K-1} = the value step K produced, T_{i+K-2} = the centre of stage K-1
+        const int rk = t - 2 * (K - 1);
         if (emit_col && rk >= j0 && rk < j1) {
             if (!LAST) {
-                P.t1_out.p[o1] = rawN;
+                P.t1_out.p[o1] = tn[K - 1];
                 P.t2_out.p[o2] = rawC[K - 1];
             }
-            P.bar.p[ob] = newacc[K - 1];
+            P.bar.p[ob] = an[K - 1];
         }
         ob += P.bar.pitch;
         if (!LAST) {
             o1 += P.t1_out.pitch;
             o2 += P.t2_out.pitch;
         }
-        // shift the windows one row north
+        // shift every window one row north; the value step q produced enters stage q as its new north row
 #pragma unroll
-        for (int s = 0; s < K; ++s) {
-            sanS[s] = sanC[s]; sanC[s] = newsan[s];
-            rawS[s] = rawC[s]; rawC[s] = newraw[s];
-            acc[s] = newacc[s];
+        for (int q = 0; q < K; ++q) {
+            const T nraw = q == 0 ? rawN0 : tn[q >= 1 ? q - 1 : 0];
+            rawSS[q] = rawS[q]; rawS[q] = rawC[q]; rawC[q] = rawN[q]; rawN[q] = nraw;
+            sanS[q] = sanC[q]; sanC[q] = sanN[q]; sanN[q] = nan2num(nraw);
+            accB[q] = accA[q]; accA[q] = an[q];
         }
-        // row t-K is not needed any more (its north faces were the south faces of row t-K+1 in step K just now)
-        if (t - K >= R0) {
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty[eslot]);
-            if (++eslot == MARCH_D) eslot = 0;
+        // releases: state row t is done (T2 / bar read above; its T1 was lifted two iterations ago); coefficient row
+        // t-2K+1 was last used as the south faces of step K's row
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            if (ti >= 0 && ti <= last_idx) mbar_arrive(&emptyS[ti & (MARCH_DS - 1)]);
+            const int ci = ti - 2 * K + 1;
+            if (ci >= 0 && ci <= last_idx) mbar_arrive(&emptyC[ci & (MARCH_DC - 1)]);
         }
         {   // swap the exchange rows
             T* tmp = xr;
