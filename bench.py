@@ -554,7 +554,10 @@ def measure(ctx, args, name, nb=0, primary=False):
         b_alg_l = 5 * w * ncomp + c_bytes_per_point(cfg["grid_type"], w) / nbl
         # algorithmic bytes of one launch = B_alg per grid-point step x points x steps the launch performs
         achieved = b_alg_l * nbl * ny * nx * dom[1] / (dom_ms * 1e-3) / 1e9
-        fk = f"fused_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)"
+        fk = (f"cgrid2_kernel ({dom[1]} Chebyshev steps per launch, rows of all arrays streamed through TMA rings)"
+              if cfg["grid_type"] == "VECTOR_C_GRID" else
+              f"vec2_kernel ({dom[1]} Chebyshev steps per launch, rows streamed through TMA rings)"
+              if ncomp == 2 else f"fused_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)")
         kname = {"fused": fk, "fused_first": fk + ", first block", "fused_last": fk + ", last block",
                  "mid": "step_kernel<MODE_MID> (one Chebyshev step)", "first": "step_kernel<MODE_FIRST>",
                  "last": "step_kernel<MODE_LAST>"}[dom[0]]
@@ -571,7 +574,7 @@ def measure(ctx, args, name, nb=0, primary=False):
                     tr = json.load(fh)
                 key = name if dom[0].startswith("fused") else name + "_onestep"
                 if key in tr:
-                    if tr[key].get("srchash") == gbuild.source_hash():
+                    if tr[key].get("srchash") == gbuild.source_hash(tr[key].get("files")):
                         roofline["traffic"] = tr[key]["bytes_per_pt_step"] * nbl * ny * nx * dom[1]
                         roofline["traffic_source"] = tr[key]["source"]
                     else:

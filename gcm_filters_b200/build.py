@@ -8,7 +8,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libgcmf.so")
 SOURCES = ["gcmf.cu"]
-HEADERS = ["gcmf_stencils.cuh", "gcmf_internal.h", os.path.join("..", "..", "include", "gcmf.h")]
+HEADERS = ["gcmf_stencils.cuh", "gcmf_fused.cuh", "gcmf_march.cuh", "gcmf_vec2.cuh", "gcmf_internal.h",
+           os.path.join("..", "..", "include", "gcmf.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",  # separate rounding of * and +, in the reference's evaluation order
@@ -19,12 +20,14 @@ NVCC_FLAGS = [
 HASH = OUT + ".srchash"
 
 
-def source_hash():
-    """sha256 over the CUDA sources, headers and flags: identifies what a built libgcmf.so was made from."""
+def source_hash(files=None):
+    """sha256 over the CUDA sources, headers and flags: identifies what a built libgcmf.so was made from.
+    `files`: hash only these files of csrc/ (what one kernel family is made from; profiles/traffic.json uses it to tell
+    whether a committed ncu capture still describes the kernel in the tree)."""
     import hashlib
 
     h = hashlib.sha256()
-    for rel in SOURCES + ["gcmf_fused.cuh"] + HEADERS:
+    for rel in (SOURCES + HEADERS if files is None else list(files)):
         with open(os.path.join(CSRC, rel), "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

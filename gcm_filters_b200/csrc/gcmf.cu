@@ -29,6 +29,7 @@
 #include "gcmf_fused.cuh"
 #ifndef GCMF_HOSTEMU
 #include "gcmf_march.cuh"
+#include "gcmf_vec2.cuh"
 #endif
 
 using namespace gcmf;
@@ -163,7 +164,10 @@ static size_t buffer_bytes(const gcmf_plan* p, int64_t nb) {
 }
 
 static bool fused_eligible(const gcmf_plan* p);
+static bool cg2_eligible(const gcmf_plan* p);
 static bool plan_uses_fused(const gcmf_plan* p) { return p->steps_per_block != 1 && fused_eligible(p); }
+// vector plans (VECTOR_C, VECTOR_B) that run two Chebyshev steps per launch (gcmf_vec2.cuh)
+static bool plan_uses_cg2(const gcmf_plan* p) { return p->steps_per_block != 1 && cg2_eligible(p); }
 static bool is_band_plan(const gcmf_plan* p) { return !(p->desc.flags & GCMF_FLAG_WRAP_Y); }
 
 extern "C" int gcmf_plan_set_steps_per_block(gcmf_plan* p, int32_t k) {
@@ -176,7 +180,7 @@ extern "C" int gcmf_plan_set_steps_per_block(gcmf_plan* p, int32_t k) {
 
 extern "C" int gcmf_workspace_bytes(const gcmf_plan* p, int64_t nb, size_t* bytes) {
     if (!p || !bytes || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
-    *bytes = (size_t)(plan_uses_fused(p) ? 4 : 2) * p->ncomp * buffer_bytes(p, nb);
+    *bytes = (size_t)((plan_uses_fused(p) || plan_uses_cg2(p)) ? 4 : 2) * p->ncomp * buffer_bytes(p, nb);
     return GCMF_OK;
 }
 
@@ -1246,10 +1250,14 @@ static int launch_fused_kernel(gcmf_plan* pl, const FusedParams<T>& P, int64_t n
 #ifndef GCMF_HOSTEMU
 // ---- row-streaming form of the fused FLUX steps (gcmf_march.cuh) ----------------------------------------------
 // Eligible: FLUX family, no tripolar fold / cut (periodic whole grids and latitude bands), every array 16-byte aligned
-// (checked by the caller), grid at least one strip wide.  GCMF_FUSED_FORM=tile|march forces one form (A/B, tests).
+// (checked by the caller), grid at least one strip wide.  OPT-IN (GCMF_FUSED_FORM=march): measured on a B200 against
+// the tile form (profiles/variants_r02b_tile_vs_march.log, ncu_r02b_march_cfg3.*): cfg3 nb = 62: 101.58 vs 100.91 ms
+// per filter call, nb = 8: 14.90 vs 13.92 ms -- fewer shared-memory wavefronts (1.34 G vs 1.72 G per launch) but 27 %
+// more instructions and three warps per scheduler that stall on fixed-latency fp64 dependencies; the tile form stays
+// the default.
 static bool march_eligible(const gcmf_plan* pl) {
     static const char* force = getenv("GCMF_FUSED_FORM");
-    if (force && !strcmp(force, "tile")) return false;
+    if (!force || strcmp(force, "march")) return false;
     if (pl->desc.op != GCMF_OP_FLUX) return false;
     if (pl->desc.flags & (GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S)) return false;
     return pl->desc.nx >= MARCH_W;
@@ -1304,6 +1312,138 @@ template <typename T> static int launch_march(const gcmf_plan* pl, const FusedPa
     return launch_march_e<T, 3>(pl, P, st);
 }
 #endif
+
+// ---- vector operators: two Chebyshev steps per launch (gcmf_vec2.cuh) -------------------------------------------
+// Eligible: VECTOR_C / VECTOR_B on whole doubly periodic grids (latitude bands keep the one-step kernels, which carry
+// the ghost-row exchange), rows that split into 16-byte vectors, at least one strip wide, every coefficient plane
+// 16-byte aligned.  Forcing a one-step C-grid kernel form with GCMF_CGRID_KERNEL (A/B, tests) also switches it off.
+template <typename T> static bool cg2_eligible_t(const gcmf_plan* p) {
+#ifdef GCMF_HOSTEMU
+    (void)p;
+    return false;  // mbarriers + TMA: device only; the emulator runs the one-step kernels (bit-identical by construction)
+#else
+    using G = Cg2Geom<T>;
+    static const bool forced = getenv("GCMF_CGRID_KERNEL") != nullptr;
+    if (p->desc.op != GCMF_OP_VECTOR_C && p->desc.op != GCMF_OP_VECTOR_B) return false;
+    if (forced || !(p->desc.flags & GCMF_FLAG_WRAP_Y)) return false;
+    if (p->desc.nx % G::AV || p->desc.nx < G::LW || p->desc.ny < 4) return false;
+    for (int s = 0; s < p->n_planes; ++s)
+        if (!p->plane[s].p || !aligned(p->plane[s].p, p->plane[s].pitch, p->plane[s].nb > 1 ? p->plane[s].bstride : 0,
+                                       G::AV, sizeof(T)))
+            return false;
+    return true;
+#endif
+}
+static bool cg2_eligible(const gcmf_plan* p) {
+    return p->desc.dtype == GCMF_F64 ? cg2_eligible_t<double>(p) : cg2_eligible_t<float>(p);
+}
+
+#ifndef GCMF_HOSTEMU
+template <typename T, template <typename, int> class OPT, int EDGE>
+static int launch_cg2_t(const gcmf_plan* pl, const Cg2Params<T>& P, cudaStream_t st) {
+    using G = Vec2Geom<T, OPT<T, 1>::NC>;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(vec2_kernel<T, OPT, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes()));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    const int ny = P.g.ny;
+    const int64_t ctas_x = (P.g.nx + CG2_WARPS * P.cpw - 1) / (CG2_WARPS * P.cpw);
+    // Rows per band.  A band stages 4 priming rows (and pays ~2 rows of prologue) on top of its own, so bands should be
+    // tall; but one CTA per SM runs at a time, so the launch takes ceil(CTAs / SMs) rounds of the longest CTA: pick the
+    // height that minimises rounds x (rows + 6) among heights up to 64 (measured on cfg5, ms per launch: 24 rows 0.409,
+    // 36: 0.404, 48: 0.410, 59 (exactly 5 rounds): 0.400, 72: 0.436, 99 (3 rounds, the model's optimum without the
+    // cap): 0.433, 180: 0.478 -- few long CTAs end raggedly).  GCMF_CGRID_ROWS overrides (tuning, tests).
+    int ry = 0;
+    if (const char* e = getenv("GCMF_CGRID_ROWS")) ry = atoi(e);
+    if (ry <= 0) {
+        double best = 1e300;
+        const int lo = ny < 12 ? ny : 12, hi = ny < 64 ? ny : 64;
+        for (int cand = lo; cand <= hi; ++cand) {
+            const int64_t ncta = ctas_x * P.nb * ((ny + cand - 1) / cand);
+            const int64_t rounds = (ncta + pl->sm_count - 1) / pl->sm_count;
+            const double cost = (double)rounds * (cand + 6);
+            if (cost < best) {
+                best = cost;
+                ry = cand;
+            }
+        }
+    }
+    if (ry > ny) ry = ny;
+    const int64_t nbands = (ny + ry - 1) / ry;
+    const int64_t nblk = ctas_x * P.nb * nbands;
+    if (nblk > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "grid too large (%lld blocks)", (long long)nblk);
+    vec2_kernel<T, OPT, EDGE><<<(unsigned)nblk, G::NTHREADS, G::smem_bytes(), st>>>(P, (unsigned)ctas_x, ry);
+    gcmf_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCMF_OK;
+}
+template <typename T, template <typename, int> class OPT>
+static int launch_cg2(const gcmf_plan* pl, const Cg2Params<T>& P, bool first, bool last, cudaStream_t st) {
+    switch ((first ? 1 : 0) | (last ? 2 : 0)) {
+        case 0: return launch_cg2_t<T, OPT, 0>(pl, P, st);
+        case 1: return launch_cg2_t<T, OPT, 1>(pl, P, st);
+        case 2: return launch_cg2_t<T, OPT, 2>(pl, P, st);
+    }
+    return launch_cg2_t<T, OPT, 3>(pl, P, st);
+}
+#endif
+
+// steps step0 and step0+1 of a vector plan in one launch
+template <typename T>
+static int run_cg2_t(const gcmf_plan* pl, int64_t nb, int step0, const gcmf_field* t1, const gcmf_field* t2,
+                     const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st) {
+#ifdef GCMF_HOSTEMU
+    (void)pl; (void)nb; (void)step0; (void)t1; (void)t2; (void)t1o; (void)t2o; (void)bar; (void)st;
+    return gcmf_set_error(GCMF_EINVAL, "the two-step C-grid kernel is device-only");
+#else
+    using G = Cg2Geom<T>;
+    const bool first = step0 == 1, last = step0 + 1 == pl->n_steps;
+    const gcmf_field* all[5] = {t1, first ? nullptr : t2, last ? nullptr : t1o, last ? nullptr : t2o, bar};
+    for (const gcmf_field* f : all)
+        for (int k = 0; f && k < 2; ++k)
+            if (!aligned(f[k].ptr, f[k].pitch, f[k].bstride, G::AV, sizeof(T)))
+                return gcmf_set_error(GCMF_EINVAL, "fused step: fields must be 16-byte aligned with vector-multiple strides");
+    for (int k = 0; k < 2; ++k) {
+        if (bar[k].ptr == t1[k].ptr || (!first && bar[k].ptr == t2[k].ptr))
+            return gcmf_set_error(GCMF_EINVAL, "fused step: bar must not alias the inputs");
+        if (!last)
+            for (int m = 0; m < 2; ++m)  // neighbouring strips / bands read the inputs while this one stores
+                if (t1o[k].ptr == t1[m].ptr || t2o[k].ptr == t1[m].ptr ||
+                    (!first && (t1o[k].ptr == t2[m].ptr || t2o[k].ptr == t2[m].ptr)))
+                    return gcmf_set_error(GCMF_EINVAL, "fused step: outputs must not alias inputs");
+    }
+    Cg2Params<T> P;
+    memset(&P, 0, sizeof P);
+    P.g.ny = pl->desc.ny;
+    P.g.nx = pl->desc.nx;
+    P.g.flags = pl->desc.flags;
+    for (int s = 0; s < pl->n_planes; ++s) P.plane[s] = pl->plane[s];
+    for (int k = 0; k < 2; ++k) {
+        P.t1[k] = FieldRef<const T>{(const T*)t1[k].ptr, t1[k].pitch, t1[k].bstride};
+        if (!first) P.t2[k] = FieldRef<const T>{(const T*)t2[k].ptr, t2[k].pitch, t2[k].bstride};
+        if (!last) {
+            P.t1o[k] = FieldRef<T>{(T*)t1o[k].ptr, t1o[k].pitch, t1o[k].bstride};
+            P.t2o[k] = FieldRef<T>{(T*)t2o[k].ptr, t2o[k].pitch, t2o[k].bstride};
+        }
+        P.bar[k] = FieldRef<T>{(T*)bar[k].ptr, bar[k].pitch, bar[k].bstride};
+    }
+    P.c = pl->c;
+    P.p0 = pl->p[0];
+    P.pa = pl->p[step0];
+    P.pb = pl->p[step0 + 1];
+    P.nb = nb;
+    // strips of equal width: the fewest CTAs per row that 28 columns per warp allow, then the columns spread evenly
+    const int strip_max = CG2_WARPS * CG2_COLS;
+    const int ctas_x = (pl->desc.nx + strip_max - 1) / strip_max;
+    P.cpw = (pl->desc.nx + ctas_x * CG2_WARPS - 1) / (ctas_x * CG2_WARPS);
+    P.lw = CG2_WARPS * P.cpw + 2 * G::HALO;
+    if (pl->desc.op == GCMF_OP_VECTOR_B) return launch_cg2<T, BgOp>(pl, P, first, last, st);
+    return launch_cg2<T, CgOp>(pl, P, first, last, st);
+#endif
+}
 
 template <typename T>
 static int run_fused_t(gcmf_plan* pl, int64_t nb, int step0, int k, const gcmf_field* t1, const gcmf_field* t2,
@@ -1380,6 +1520,7 @@ static int run_fused_t(gcmf_plan* pl, int64_t nb, int step0, int k, const gcmf_f
 
 extern "C" int gcmf_fused_max_steps(const gcmf_plan* p) {
     if (!p) return 0;
+    if (cg2_eligible(p)) return 2;
     return fused_eligible(p) ? FusedGeom<double>::H : 0;
 }
 
@@ -1388,6 +1529,25 @@ extern "C" int gcmf_cheb_fused(gcmf_plan* p, int64_t nb, int32_t step, int32_t k
                                const gcmf_field* bar, void* stream) {
     if (!p || nb < 1) return gcmf_set_error(GCMF_EINVAL, "bad argument");
     if (p->n_steps < 2) return gcmf_set_error(GCMF_ESTATE, "gcmf_plan_set_filter has not been called");
+    if (cg2_eligible(p)) {
+        // vector operators: exactly two steps per launch; a trailing single step (odd n_steps) is the one-step LAST kernel
+        if (k == 1 && step == p->n_steps) return gcmf_cheb_step(p, nb, step, t1_in, t2_in, t1_out, bar, stream);
+        if (k != 2) return gcmf_set_error(GCMF_EINVAL, "vector plans fuse exactly 2 steps (k = %d)", k);
+        if (step < 1 || step + 1 > p->n_steps)
+            return gcmf_set_error(GCMF_EINVAL, "fused steps %d..%d must lie inside 1..%d", step, step + 1, p->n_steps);
+        TRY(check_planes(p));
+        TRY(check_fields(p, t1_in, "t1_in"));
+        if (step > 1) TRY(check_fields(p, t2_in, "t2_in"));
+        if (step + 1 < p->n_steps) {
+            TRY(check_fields(p, t1_out, "t1_out"));
+            TRY(check_fields(p, t2_out, "t2_out"));
+        }
+        TRY(check_fields(p, bar, "bar"));
+        CUDA_TRY(cudaSetDevice(p->desc.device));
+        if (p->desc.dtype == GCMF_F64)
+            return run_cg2_t<double>(p, nb, step, t1_in, t2_in, t1_out, t2_out, bar, (cudaStream_t)stream);
+        return run_cg2_t<float>(p, nb, step, t1_in, t2_in, t1_out, t2_out, bar, (cudaStream_t)stream);
+    }
     if (!fused_eligible(p)) return gcmf_set_error(GCMF_EINVAL, "this plan has no fused path (see gcmf_fused_max_steps)");
     if (k < 1 || k > FusedGeom<double>::H) return gcmf_set_error(GCMF_EINVAL, "k = %d outside 1..%d", k, FusedGeom<double>::H);
     if (step < 1 || step + k - 1 > p->n_steps)
@@ -1463,6 +1623,32 @@ extern "C" int gcmf_filter(gcmf_plan* p, int64_t nb, const gcmf_field* in, const
             i += kk;
         }
         return GCMF_OK;
+    }
+    if (plan_uses_cg2(p)) {
+        // vector operators, temporally blocked: the recurrence (filter.py:225-283) as n/2 two-step launches (+ the one-step LAST
+        // kernel when n is odd).  State ping-pongs between two workspace pairs; the user's input is only read.
+        bool ok = true;
+        for (int k = 0; ok && k < nc; ++k)
+            ok = aligned(out[k].ptr, out[k].pitch, out[k].bstride, (int)(16 / es), es) &&
+                 aligned(in[k].ptr, in[k].pitch, in[k].bstride, (int)(16 / es), es);
+        if (ok) {
+            gcmf_field pair[2][2][2];
+            for (int j = 0; j < 4; ++j)
+                for (int k = 0; k < nc; ++k)
+                    pair[j >> 1][j & 1][k] = gcmf_field{(char*)workspace + (size_t)(j * nc + k) * bb, pitch, bs};
+            const gcmf_field* T1 = X;
+            const gcmf_field* T2 = X;
+            int cur = 0;
+            for (int i = 1; i <= n;) {
+                const int kk = (n - i + 1) < 2 ? 1 : 2;
+                TRY(gcmf_cheb_fused(p, nb, i, kk, T1, T2, pair[cur][0], pair[cur][1], out, stream));
+                T1 = pair[cur][0];
+                T2 = pair[cur][1];
+                cur ^= 1;
+                i += kk;
+            }
+            return GCMF_OK;
+        }
     }
     // step 1: T1 = A(x) -> A ; bar = p0 x + p1 T1 -> out        (filter.py:191-195)
     TRY(gcmf_cheb_step(p, nb, 1, X, nullptr, A, out, stream));

@@ -502,3 +502,45 @@ def test_cgrid_kernel_forms_are_bit_identical(kernel):
             res[k] = dict(np.load(path))
         for key in res["tiled"]:
             assert np.array_equal(res["tiled"][key], res[kernel][key], equal_nan=True), (kernel, key)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,nb,n_steps", [((70, 488), 2, 6), ((37, 250), 1, 7), ((64, 1000), 3, 5), ((12, 232), 1, 3),
+                                               ((130, 456), 1, 9)])
+@pytest.mark.parametrize("g", ["VECTOR_C_GRID", "VECTOR_B_GRID"])
+def test_vector_two_step_kernel_is_bit_identical_to_one_step(g, shape, nb, n_steps, dtype, monkeypatch):
+    """Temporal blocking of the vector operators (vec2_kernel: steps i and i+1 in one launch, step i+1 marching one row
+    behind step i): same expressions in the same order as two one-step launches -> identical bits.  Even and odd step
+    counts (a trailing one-step LAST launch), one and several column strips, bands shorter than the priming depth,
+    NaNs in the input, both dtypes; half as many launches as steps."""
+    from gcm_filters_b200 import engine
+    (u, v), gv = fixtures.fixture(g, shape)
+    rng = np.random.default_rng(5)
+    us = np.stack([u * (1 + 0.1 * k) + 0.01 * rng.standard_normal(shape) for k in range(nb)]).astype(dtype)
+    vs = np.stack([v - 0.2 * k * u for k in range(nb)]).astype(dtype)
+    us[0, 3:5, 7:9] = np.nan  # nan_to_num inside both steps
+    gvt = {k: np.asarray(a).astype(dtype) for k, a in gv.items()}
+    fa = vec_args(g, gv, dict(filter_scale=6.0, dx_min=1.0, n_steps=n_steps))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        flt = make_filter(g, gvt, **fa)
+    assert flt.n_steps == n_steps
+    lib = _cabi.get_library()
+    av = 16 // np.dtype(dtype).itemsize  # rows must split into 16-byte vectors and span one strip (28 x 8 + halo)
+    blocked = shape[1] % av == 0 and (shape[0] * shape[1]) % av == 0 and shape[1] >= 224 + 2 * max(2, av)
+    for rows in (None, "5", "16"):  # default band height, bands of 5 rows (shorter than the 4 priming rows + 2), 16
+        if rows:
+            monkeypatch.setenv("GCMF_CGRID_ROWS", rows)
+        n0 = lib.launch_count()
+        fu, fv = flt.apply_to_vector(us, vs, None)
+        launches = lib.launch_count() - n0
+        monkeypatch.delenv("GCMF_CGRID_ROWS", raising=False)
+        assert launches == ((n_steps + 1) // 2 if blocked else n_steps), (launches, n_steps, blocked)
+        try:
+            engine.set_steps_per_block(1)
+            pu, pv = flt.apply_to_vector(us, vs, None)
+        finally:
+            engine.set_steps_per_block(0)
+        assert fu.dtype == dtype
+        assert np.array_equal(fu, pu, equal_nan=True) and np.array_equal(fv, pv, equal_nan=True), rows

@@ -1,0 +1,23 @@
+# GPU call 3: A/B of the two-step C-grid kernel variants (LAG 1/2, 8/7 consumer warps): parity test, then cfg5 timing
+mkdir -p gpurun_out
+cp gcm_filters_b200/libgcmf.so /tmp/libgcmf_intree.so
+B="python bench.py --workload cfg5 --steps 10 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-secondary --no-e2e-numpy"
+pick() { python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); r=d.get('roofline',{})
+        print('$1', 'ms_per_call', round(d['ms_per_step'],4), 'Gpts/s', round(d['value']/1e9,2), 'mix', r.get('launch_mix_ms'))
+"; }
+: > gpurun_out/c3_ab.log
+for n in intree "$@"; do
+    if [ "$n" = intree ]; then cp /tmp/libgcmf_intree.so gcm_filters_b200/libgcmf.so; else cp "build/variants/libgcmf_$n.so" gcm_filters_b200/libgcmf.so; fi
+    timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "two_step" > gpurun_out/c3_tests_$n.log 2>&1
+    echo "$n tests: $(tail -1 gpurun_out/c3_tests_$n.log)" >> gpurun_out/c3_ab.log
+    $B | pick ${n}_auto >> gpurun_out/c3_ab.log 2>&1
+    for r in 30 44 59; do GCMF_CGRID_ROWS=$r $B | pick ${n}_rows$r >> gpurun_out/c3_ab.log 2>&1; done
+    python bench.py --workload cfgb --steps 10 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-secondary --no-e2e-numpy | pick ${n}_cfgb >> gpurun_out/c3_ab.log 2>&1
+done
+cp /tmp/libgcmf_intree.so gcm_filters_b200/libgcmf.so
+python bench.py --workload cfgb --steps-per-block 1 --steps 10 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-secondary --no-e2e-numpy | pick onestep_cfgb >> gpurun_out/c3_ab.log 2>&1
+cat gpurun_out/c3_ab.log
