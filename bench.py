@@ -598,16 +598,18 @@ def free_device(ctx):
     ctx.torch.cuda.empty_cache()
 
 
-def banded_secondary(ctx, args):
-    """cfg5 (VECTOR_C_GRID 2160 x 4320) as latitude bands, one per GPU, ghost rows stored by the step kernels straight
-    into the neighbours' peer memory (strong scaling of one 2-D field)."""
+def banded_secondary(ctx, args, fused=False):
+    """cfg5 (VECTOR_C_GRID 2160 x 4320) as latitude bands, one per GPU (strong scaling of one 2-D field).  fused=False:
+    one-step kernels that store their border rows straight into the neighbours' peer memory (PeerBandedFilter);
+    fused=True: the two-step kernel on bands with two ghost rows per side, pulled from the neighbours' peer memory once
+    per two-step block (FusedBandedFilter, exchange="peer")."""
     from gcm_filters_b200 import _cabi
-    from gcm_filters_b200.scheduler import PeerBandedFilter
+    from gcm_filters_b200.scheduler import FusedBandedFilter, PeerBandedFilter
 
     torch = ctx.torch
     cfg = build_workload("cfg5")
     flt = make_filter(cfg)
-    bf = PeerBandedFilter(flt, ctx.rank, ctx.world)
+    bf = FusedBandedFilter(flt, ctx.rank, ctx.world, exchange="peer") if fused else PeerBandedFilter(flt, ctx.rank, ctx.world)
     st = bf.stage(*cfg["fields"])
     lib = _cabi.get_library()
     f0 = cfg["fields"][0]
@@ -631,8 +633,11 @@ def banded_secondary(ctx, args):
     b_alg = 5 * 8 * 2 + c_bytes_per_point("VECTOR_C_GRID", 8)
     return {"workload": config_of(cfg, n_steps, (ny, nx), f0.dtype)["workload"], "value": value,
             "ms_per_step": ms / steps, "n_steps": n_steps, "whole_call_frac": b_alg * value / ctx.world / 1e9 / peak,
-            "sharding": f"{ctx.world} latitude band(s); ghost rows stored by the step kernels into the neighbours' peer "
-                        f"memory over NVLink, flag-synchronised (no NCCL on the data path)"}
+            "sharding": (f"{ctx.world} latitude band(s); two Chebyshev steps per launch on bands with 2 ghost rows per side, "
+                         f"pulled from the neighbours' peer memory over NVLink once per block (no NCCL on the data path)"
+                         if fused else
+                         f"{ctx.world} latitude band(s); ghost rows stored by the step kernels into the neighbours' peer "
+                         f"memory over NVLink, flag-synchronised (no NCCL on the data path)")}
 
 
 def gpu_arm(args):
@@ -669,10 +674,13 @@ def gpu_arm(args):
                 secondary.append({"workload": name, "error": f"{type(e).__name__}: {e}"})
         if ctx.world > 1:
             free_device(ctx)
-            try:
-                secondary.append(banded_secondary(ctx, args))
-            except Exception as e:  # noqa: BLE001
-                secondary.append({"workload": "cfg5 banded", "error": f"{type(e).__name__}: {e}"})
+            for fused in (False, True):
+                try:
+                    secondary.append(banded_secondary(ctx, args, fused=fused))
+                except Exception as e:  # noqa: BLE001
+                    secondary.append({"workload": "cfg5 banded" + (" (two-step blocks)" if fused else ""),
+                                      "error": f"{type(e).__name__}: {e}"})
+                free_device(ctx)
     ctx.close()
     if ctx.rank != 0:
         return
@@ -715,6 +723,7 @@ def banded_arm(args):
     f0 = cfg["fields"][0]
     ny, nx = f0.shape[-2:]
     nb = st["nb"]
+    H = st.get("H", 1)
     w = f0.dtype.itemsize
     lib = _cabi.get_library()
 
@@ -764,8 +773,9 @@ def banded_arm(args):
         "dtype": "f64" if w == 8 else "f32", "data": DATA,
         "config": dict(config_of(cfg, n_steps, f0.shape, f0.dtype),
                        sharding=f"{world} latitude band(s), " +
-                       ("4 ghost rows, fused 4-step blocks, ghost rows pulled from peer memory once per block" if args.fused and args.peer
-                        else "4 ghost rows, fused 4-step blocks, one NCCL exchange per block" if args.fused else
+                       (f"{H} ghost rows, fused {H}-step blocks, ghost rows pulled from peer memory once per block"
+                        if args.fused and args.peer else
+                        f"{H} ghost rows, fused {H}-step blocks, one NCCL exchange per block" if args.fused else
                         "ghost rows stored by the step kernels into the neighbours' peer memory (NVLink), flag-synchronised"
                         if args.peer else "NCCL send/recv per Chebyshev step")),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

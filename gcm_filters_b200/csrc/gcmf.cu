@@ -1314,9 +1314,10 @@ template <typename T> static int launch_march(const gcmf_plan* pl, const FusedPa
 #endif
 
 // ---- vector operators: two Chebyshev steps per launch (gcmf_vec2.cuh) -------------------------------------------
-// Eligible: VECTOR_C / VECTOR_B on whole doubly periodic grids (latitude bands keep the one-step kernels, which carry
-// the ghost-row exchange), rows that split into 16-byte vectors, at least one strip wide, every coefficient plane
-// 16-byte aligned.  Forcing a one-step C-grid kernel form with GCMF_CGRID_KERNEL (A/B, tests) also switches it off.
+// Eligible: VECTOR_C / VECTOR_B on whole doubly periodic grids (gcmf_filter) and on latitude bands (gcmf_cheb_fused on a
+// band plan: the caller keeps TWO ghost rows of the fields and of every plane on each side and refreshes those of
+// T_{i+1} and T_i after every block), rows that split into 16-byte vectors, at least one strip wide, every coefficient
+// plane 16-byte aligned.  Forcing a one-step C-grid kernel form with GCMF_CGRID_KERNEL (A/B, tests) switches it off.
 template <typename T> static bool cg2_eligible_t(const gcmf_plan* p) {
 #ifdef GCMF_HOSTEMU
     (void)p;
@@ -1325,7 +1326,7 @@ template <typename T> static bool cg2_eligible_t(const gcmf_plan* p) {
     using G = Cg2Geom<T>;
     static const bool forced = getenv("GCMF_CGRID_KERNEL") != nullptr;
     if (p->desc.op != GCMF_OP_VECTOR_C && p->desc.op != GCMF_OP_VECTOR_B) return false;
-    if (forced || !(p->desc.flags & GCMF_FLAG_WRAP_Y)) return false;
+    if (forced) return false;
     if (p->desc.nx % G::AV || p->desc.nx < G::LW || p->desc.ny < 4) return false;
     for (int s = 0; s < p->n_planes; ++s)
         if (!p->plane[s].p || !aligned(p->plane[s].p, p->plane[s].pitch, p->plane[s].nb > 1 ? p->plane[s].bstride : 0,

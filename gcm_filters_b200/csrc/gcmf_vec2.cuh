@@ -6,15 +6,18 @@
 // in -- u, v, 14 coefficient planes, T_{i-2}, bar -- and 4 rows out per row of points = 192 B per grid-point step at
 // nb = 1).  The only way below that is to do more steps per byte.  This kernel keeps the row-streaming shape of
 // cgrid_tma_kernel -- a CTA owns a strip of columns and marches north through a band of rows -- and runs step i+1
-// LAG rows behind step i inside the same march:
+// ONE ROW behind step i inside the same march:
 //
 //   iteration s (row j = R0 + s):   step i   consumes input row j+1 from the ring and produces T_i(j)          (registers)
-//                                   step i+1 consumes T_i(j) [LAG 1] or T_i(j-1) [LAG 2] as its "row j+1" and
-//                                            produces T_{i+1}(j-LAG)                                            (registers)
+//                                   step i+1 consumes T_i(j) as its "row j+1" and produces T_{i+1}(j-1)         (registers)
+//
+// (A two-row lag -- step i+1 consuming T_i one iteration later, so that the two chains of an iteration are independent --
+// was measured and is gone: cfg5 0.409 vs 0.400 ms per launch; it costs a coefficient-ring slot and the consumers are not
+// what the launch waits for.)
 //
 // Both steps are the same marching recurrence (an operator policy: the state of "row j" lives in registers, W / E
 // neighbours come from the adjacent lanes by warp shuffle), fed from shared memory (step i) or from the registers step i
-// wrote (step i+1).  The coefficient rows are staged ONCE for both steps (a row lives for 2 + LAG iterations in its ring
+// wrote (step i+1).  The coefficient rows are staged ONCE for both steps (a row lives for three iterations in its ring
 // instead of two), T_i never touches HBM on its way into step i+1:
 //
 //   C-grid, per 2 steps and row: 20 rows read + 6 rows written (T_{i+1}, T_i, bar) = 104 B per grid-point step (192: x 1.85)
@@ -23,7 +26,11 @@
 // Halo: a warp's 32 lanes see 30 valid columns after step i and 28 after step i+1 (lanes 2..29 emit); a band primes with
 // two extra rows on either side.  Two rings (TMA bulk copies, cp.async.bulk -> UBLKCP, one lane per array, mbarrier
 // complete_tx / consumer-release "empty" barriers as in cgrid_tma_kernel): the 6 field rows are released after one
-// iteration, the coefficient rows after 1 + LAG.
+// iteration, the coefficient rows after two.
+//
+// Whole periodic grids, or a latitude band of a decomposed domain (no GCMF_FLAG_WRAP_Y): rows -2, -1 and ny, ny+1 of
+// the fields and of every coefficient plane are then ghost rows present in memory, which the caller refreshes once per
+// two-step block (scheduler.FusedBandedFilter).
 //
 // Same expressions in the same order as the one-step kernels: results are bit-identical to two gcmf_cheb_step calls.
 // Device-only (mbarriers + TMA); the host emulator takes the one-step path, which the GPU tests compare against.
@@ -35,16 +42,23 @@ namespace gcmf {
 #ifndef GCMF_CG2_WARPS
 #define GCMF_CG2_WARPS 8
 #endif
-#ifndef GCMF_CG2_LAG
-#define GCMF_CG2_LAG 1  // rows between step i and step i+1: 1 = step i+1 consumes T_i(j) in the iteration that made it;
-#endif                  // 2 = one iteration later (two independent chains per iteration, one more coefficient row live)
+// Ring depths, measured on cfg5 / the same geometry for the B-grid (ms per two-step launch): 5 field + 6 coefficient
+// slots 0.3356 / 0.2513 (B-grid: 8 coefficient slots), 4 + 7: 0.3386 / 0.2706; consumer loop unrolled x1 0.346, x2 0.3386,
+// x4 0.3348 (166 registers).
 #ifndef GCMF_CG2_FS
-#define GCMF_CG2_FS (GCMF_CG2_LAG == 1 ? 5 : 4)   // field ring slots (a row is live for 2 iterations)
+#define GCMF_CG2_FS 5   // field ring slots (a row is live for 2 iterations)
 #endif
 #ifndef GCMF_CG2_CS
-#define GCMF_CG2_CS (GCMF_CG2_LAG == 1 ? 6 : 7)   // coefficient ring slots, 14 arrays (a row is live for 2 + LAG iterations)
+#define GCMF_CG2_CS 6   // coefficient ring slots, 14 arrays (a row is live for 3 iterations)
 #endif
-constexpr int CG2_WARPS = GCMF_CG2_WARPS;  // consumer warps per CTA (+ 1 producer warp)
+#ifndef GCMF_CG2_UNROLL
+#define GCMF_CG2_UNROLL 2  // consumer loop unrolled by two: the row-state rotation becomes register renaming
+#endif
+#ifndef GCMF_CG2_UNROLL
+#define GCMF_CG2_UNROLL 2  // consumer loop unrolled by two: the row-state rotation becomes register renaming
+#endif
+constexpr int CG2_UNROLL = GCMF_CG2_UNROLL;
+constexpr int CG2_WARPS = GCMF_CG2_WARPS;  // consumer warps per CTA (+ 2 producer warps)
 constexpr int CG2_COLS = 28;               // at most 28 output columns per warp (lanes 2..29)
 
 template <typename T, int NC_> struct Vec2Geom {
@@ -54,7 +68,7 @@ template <typename T, int NC_> struct Vec2Geom {
     static constexpr int NC = NC_, NF = 6;                   // coefficient arrays; field arrays: u, v, t2u, t2v, bar_u, bar_v
     static constexpr int FS = GCMF_CG2_FS;
     static constexpr int CS = NC_ > 8 ? GCMF_CG2_CS : GCMF_CG2_CS + 2;  // fewer planes: a deeper ring fits
-    static constexpr int NTHREADS = 32 * (CG2_WARPS + 1);
+    static constexpr int NTHREADS = 32 * (CG2_WARPS + 2);  // consumers + the two producer warps
     static constexpr size_t SMEM = ((size_t)FS * NF + (size_t)CS * NC) * LW * sizeof(T) + 2 * (FS + CS) * sizeof(uint64_t) + 128;
     static_assert(SMEM <= 232448, "rings exceed the 227 KB of shared memory a CTA may use");
     static_assert(NC_ + 6 <= 32, "one producer lane per array");
@@ -165,15 +179,43 @@ template <typename T, int LW> struct BgOp {
     }
 };
 
+// mbarrier helpers on 32-bit shared-memory addresses (the consumers keep the barrier addresses in registers)
+__device__ __forceinline__ void mbar_wait_a(uint32_t mb, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(mb), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t mb) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+}
+// position of a staged row in a ring of N slots, advanced without division: slot index and phase parity of its barriers
+template <int N> struct RingPos {
+    int slot;
+    unsigned phase;
+    __device__ __forceinline__ void next() {
+        if (++slot == N) {
+            slot = 0;
+            phase ^= 1u;
+        }
+    }
+};
+
 // EDGE bit 0: the block starts at recurrence step 1 (t1 = prepared input, no T_{i-2}, no bar yet);
 // EDGE bit 1: the block ends at step n_steps (no T is stored).
+// Warps 0..CG2_WARPS-1 consume; warp CG2_WARPS streams the field ring, warp CG2_WARPS+1 the coefficient ring (each at
+// its own pace: the field rows are released one iteration earlier than the coefficient rows).
 template <typename T, template <typename, int> class OPT, int EDGE>
-__global__ void __launch_bounds__(32 * (CG2_WARPS + 1), 1) vec2_kernel(const __grid_constant__ Cg2Params<T> P, unsigned ctas_x, int ry) {
+__global__ void __launch_bounds__(32 * (CG2_WARPS + 2), 1) vec2_kernel(const __grid_constant__ Cg2Params<T> P, unsigned ctas_x, int ry) {
     using OP = OPT<T, Vec2Geom<T, 14>::LW>;
     using G = Vec2Geom<T, OP::NC>;
     constexpr bool FIRST = (EDGE & 1) != 0, LAST = (EDGE & 2) != 0;
-    constexpr int LW = G::LW, FS = G::FS, CS = G::CS, LAG = GCMF_CG2_LAG;
-    static_assert(LAG == 1 || LAG == 2, "GCMF_CG2_LAG");
+    constexpr int LW = G::LW, FS = G::FS, CS = G::CS;
     constexpr int FSLOT = G::NF * LW, CSLOT = G::NC * LW;
     extern __shared__ __align__(128) unsigned char cg2_smem[];
     T* fring = reinterpret_cast<T*>(cg2_smem);
@@ -201,71 +243,71 @@ __global__ void __launch_bounds__(32 * (CG2_WARPS + 1), 1) vec2_kernel(const __g
     // staged rows R0 .. j1+1: step i+1 emits rows j0 .. j1-1, needs T_i on j0-1 .. j1, which needs the input on j0-2 .. j1+1
     const int R0 = j0 - 2;
     const int nstage = (j1 - j0) + 4;
-    auto rowidx = [&](int r) { return r < 0 ? r + ny : (r >= ny ? r - ny : r); };  // periodic y (ny >= 4)
     const int strip = CG2_WARPS * P.cpw;  // output columns per CTA
 
-    if (warp == CG2_WARPS) {
-        // ---- producer warp: lane a owns one array and issues that array's row copy.
-        //   lanes 0, 1: u, v     lanes 2..NC+1: the coefficient planes     NC+2, NC+3: T_{i-2}     NC+4, NC+5: bar
+    if (warp >= CG2_WARPS) {
+        // ---- producer warps: lane a owns one array and issues that array's row copy
+        //   field warp:        lanes 0, 1: u, v (every row)   2, 3: T_{i-2} (rows j0-1 .. j1)   4, 5: bar (rows j0 .. j1-1)
+        //   coefficient warp:  lanes 0 .. NC-1: the coefficient planes
+        const bool coef = warp == CG2_WARPS + 1;
+        // row r of the arrays: periodic y (ny >= 4), or a latitude band whose two ghost rows per side are present in memory
+        const bool wrap = (P.g.flags & FL_WRAP_Y) != 0;
+        auto rowidx = [&](int r) { return wrap ? (r < 0 ? r + ny : (r >= ny ? r - ny : r)) : r; };
         const T* base = nullptr;
         int64_t pitch = 0;
-        int kind = -1;  // 0: field (every row), 1: coefficient, 2: T_{i-2} (rows j0-1 .. j1), 3: bar (rows j0 .. j1-1)
-        T* dst0 = nullptr;
-        if (lane < 2) {
+        int kind = -1;  // 0: every row, 2: T_{i-2}, 3: bar
+        if (coef) {
+#pragma unroll
+            for (int k = 0; k < G::NC; ++k)
+                if (lane == k) {
+                    base = plane_base<T>(P.plane[k], b);
+                    pitch = P.plane[k].pitch;
+                    kind = 0;
+                }
+        } else if (lane < 2) {
             base = P.t1[lane].p + (int64_t)b * P.t1[lane].bstride;
             pitch = P.t1[lane].pitch;
             kind = 0;
-            dst0 = fring + lane * LW;
+        } else if (!FIRST && lane < 4) {
+            base = P.t2[lane - 2].p + (int64_t)b * P.t2[lane - 2].bstride;
+            pitch = P.t2[lane - 2].pitch;
+            kind = 2;
+        } else if (!FIRST && lane < 6) {
+            base = P.bar[lane - 4].p + (int64_t)b * P.bar[lane - 4].bstride;
+            pitch = P.bar[lane - 4].pitch;
+            kind = 3;
         }
-#pragma unroll
-        for (int k = 0; k < G::NC; ++k)
-            if (lane == 2 + k) {
-                base = plane_base<T>(P.plane[k], b);
-                pitch = P.plane[k].pitch;
-                kind = 1;
-                dst0 = cring + k * LW;
-            }
-        if (!FIRST) {
-            constexpr int L2 = G::NC + 2, LB = G::NC + 4;
-            if (lane == L2 || lane == L2 + 1) {
-                base = P.t2[lane - L2].p + (int64_t)b * P.t2[lane - L2].bstride;
-                pitch = P.t2[lane - L2].pitch;
-                kind = 2;
-                dst0 = fring + (2 + lane - L2) * LW;
-            }
-            if (lane == LB || lane == LB + 1) {
-                base = P.bar[lane - LB].p + (int64_t)b * P.bar[lane - LB].bstride;
-                pitch = P.bar[lane - LB].pitch;
-                kind = 3;
-                dst0 = fring + (4 + lane - LB) * LW;
-            }
-        }
+        T* const ring = coef ? cring : fring;
+        uint64_t* const full = coef ? fullC : fullF;
+        uint64_t* const empty = coef ? emptyC : emptyF;
+        const int nslot = coef ? CS : FS, slot_elems = coef ? CSLOT : FSLOT;
+        T* const dst0 = ring + lane * LW;
         const int col0 = cx * strip - G::HALO;
         const int gx = col0 < 0 ? col0 + nx : col0;
         const int lw = P.lw;
         const int n1 = (nx - gx) < lw ? (nx - gx) : lw;
         const unsigned rowb = (unsigned)(lw * sizeof(T));
+        int slot = 0;
+        unsigned phase = 0;  // parity of the "empty" phase the producer waits for (second lap: 0, third: 1, ...)
         for (int q = 0; q < nstage; ++q) {
-            const int sf = q % FS, sc = q % CS;
-            if (q >= FS) mbar_wait(&emptyF[sf], (unsigned)(((q / FS) - 1) & 1));
-            if (q >= CS) mbar_wait(&emptyC[sc], (unsigned)(((q / CS) - 1) & 1));
-            if (q >= FS || q >= CS) fence_proxy_async();
-            const int r = R0 + q;
+            if (q >= nslot) {
+                mbar_wait(&empty[slot], phase);
+                fence_proxy_async();
+            }
             const bool has_t2 = !FIRST && q >= 1 && q <= nstage - 2;
             const bool has_bar = !FIRST && q >= 2 && q <= nstage - 3;
-            if (lane == 0) {
-                mbar_expect_tx(&fullF[sf], rowb * (2u + (has_t2 ? 2u : 0u) + (has_bar ? 2u : 0u)));
-                mbar_expect_tx(&fullC[sc], rowb * (unsigned)G::NC);
-            }
+            if (lane == 0)
+                mbar_expect_tx(&full[slot], coef ? rowb * (unsigned)G::NC : rowb * (2u + (has_t2 ? 2u : 0u) + (has_bar ? 2u : 0u)));
             __syncwarp();
-            const bool go = kind == 0 || kind == 1 || (kind == 2 && has_t2) || (kind == 3 && has_bar);
-            if (go) {
-                const T* row = base + (int64_t)rowidx(r) * pitch;
-                const bool coef = kind == 1;
-                T* dst = dst0 + (coef ? (size_t)sc * CSLOT : (size_t)sf * FSLOT);
-                uint64_t* fb = coef ? &fullC[sc] : &fullF[sf];
-                bulk_copy_g2s(dst, row + gx, (unsigned)(n1 * sizeof(T)), fb);
-                if (n1 < lw) bulk_copy_g2s(dst + n1, row, (unsigned)((lw - n1) * sizeof(T)), fb);
+            if (kind == 0 || (kind == 2 && has_t2) || (kind == 3 && has_bar)) {
+                const T* row = base + (int64_t)rowidx(R0 + q) * pitch;
+                T* dst = dst0 + (size_t)slot * slot_elems;
+                bulk_copy_g2s(dst, row + gx, (unsigned)(n1 * sizeof(T)), &full[slot]);
+                if (n1 < lw) bulk_copy_g2s(dst + n1, row, (unsigned)((lw - n1) * sizeof(T)), &full[slot]);
+            }
+            if (++slot == nslot) {
+                slot = 0;
+                if (q >= nslot) phase ^= 1u;
             }
         }
         return;
@@ -276,97 +318,94 @@ __global__ void __launch_bounds__(32 * (CG2_WARPS + 1), 1) vec2_kernel(const __g
     const int i = cx * strip + warp * P.cpw + lane - 2;            // global column (unwrapped; < 0 or >= nx: never emitted)
     const bool emit = lane >= 2 && lane < 2 + P.cpw && i >= 0 && i < nx;
     const T cc = (T)P.c;
-    auto frow = [&](int q) { return fring + (size_t)(q % FS) * FSLOT + lc; };
-    auto crow = [&](int q) { return cring + (size_t)(q % CS) * CSLOT + lc; };
+    const T* const fcol = fring + lc;
+    const T* const ccol = cring + lc;
+    const uint32_t fullF_a = smem_u32(fullF), emptyF_a = smem_u32(emptyF), fullC_a = smem_u32(fullC), emptyC_a = smem_u32(emptyC);
     typename OP::Row S1, S2;
     OP::zero(S2);
     {   // prologue: row R0 becomes the state of step i
-        mbar_wait(&fullF[0], 0);
-        mbar_wait(&fullC[0], 0);
-        OP::init(S1, frow(0), crow(0));
+        mbar_wait_a(fullF_a, 0);
+        mbar_wait_a(fullC_a, 0);
+        OP::init(S1, fcol, ccol);
     }
-    // delay lines between the two steps: T_{i-1} and bar-after-step-i of the rows step i+1 has not emitted yet, and (LAG 2)
-    // the T_i row step i+1 consumes one iteration after step i produced it
-    T xd[LAG][2], bd[LAG][2], tnd[2] = {T(0), T(0)};
+    // between the two steps: T_{i-1} and bar-after-step-i of the row step i+1 emits in the next iteration
+    T xd[2] = {T(0), T(0)}, bd[2] = {T(0), T(0)};
+    T* pb[2];
+    T* p1[2] = {nullptr, nullptr};
+    T* p2[2] = {nullptr, nullptr};
 #pragma unroll
-    for (int d = 0; d < LAG; ++d) xd[d][0] = xd[d][1] = bd[d][0] = bd[d][1] = T(0);
-    int64_t o1[2] = {0, 0}, o2[2] = {0, 0}, ob[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {  // running element offsets of the output row (starts at row j0 with the first emission)
-        ob[k] = (int64_t)b * P.bar[k].bstride + (int64_t)j0 * P.bar[k].pitch + i;
+    for (int k = 0; k < 2; ++k) {  // output row pointers (row j0 at the first emission, s = 3)
+        pb[k] = P.bar[k].p + ((int64_t)b * P.bar[k].bstride + (int64_t)j0 * P.bar[k].pitch + i);
         if (!LAST) {
-            o1[k] = (int64_t)b * P.t1o[k].bstride + (int64_t)j0 * P.t1o[k].pitch + i;
-            o2[k] = (int64_t)b * P.t2o[k].bstride + (int64_t)j0 * P.t2o[k].pitch + i;
+            p1[k] = P.t1o[k].p + ((int64_t)b * P.t1o[k].bstride + (int64_t)j0 * P.t1o[k].pitch + i);
+            p2[k] = P.t2o[k].p + ((int64_t)b * P.t2o[k].bstride + (int64_t)j0 * P.t2o[k].pitch + i);
         }
     }
-    // step i+1 on the T_i row (un, vn): its state row is LAG rows behind step i's; emits one output row from iteration
-    // 2 + LAG on (row j0)
-    auto step2 = [&](int s, T un, T vn) {
-        T lap2[2], x2[2];
-        OP::row(S2, un, vn, crow(s - LAG + 1), crow(s - LAG), lap2, x2);
-        if (s >= 2 + LAG) {
-            if (emit) {
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const T a2 = -x2[k] - cc * lap2[k];
-                    const T t = cheb_next<T>(a2, xd[LAG - 1][k]);
-                    if (!LAST) {
-                        P.t1o[k].p[o1[k]] = t;
-                        P.t2o[k].p[o2[k]] = x2[k];
-                    }
-                    P.bar[k].p[ob[k]] = (T)bar_update((double)bd[LAG - 1][k], P.pb, (double)t);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                ob[k] += P.bar[k].pitch;
-                if (!LAST) { o1[k] += P.t1o[k].pitch; o2[k] += P.t2o[k].pitch; }
-            }
-        }
-    };
-    const int niter = nstage - 2 + LAG;
-    for (int s = 0; s < niter; ++s) {
-        const int sn = s + 1;
-        const bool has_next = sn < nstage;  // (LAG 2: the last iteration only drains step i+1)
-        if (has_next) {
-            mbar_wait(&fullF[sn % FS], (unsigned)((sn / FS) & 1));
-            mbar_wait(&fullC[sn % CS], (unsigned)((sn / CS) & 1));
-        }
-        // LAG 2: step i+1 consumes the T_i row of the PREVIOUS iteration -- independent of this iteration's step i, so the
-        // two dependent fp64 chains of an iteration overlap
-        if (LAG == 2 && s >= 2) step2(s, tnd[0], tnd[1]);
-        T x[2] = {T(0), T(0)}, tn[2] = {T(0), T(0)}, b1[2] = {T(0), T(0)};
-        if (has_next) {
-            // ---- step i at row j = R0 + s (valid from s = 1 on: rows j0-1 .. j1)
-            const T* fn = frow(sn);
-            const T* fc = frow(s);
-            T lap[2];
-            OP::row(S1, fn[0], fn[LW], crow(sn), crow(s), lap, x);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const T a = -x[k] - cc * lap[k];                                   // filter.py:232-236
-                if (FIRST) {
-                    tn[k] = a;
-                    b1[k] = (T)bar_update(P.p0 * (double)x[k], P.pa, (double)a);   // filter.py:253-254
-                } else {
-                    tn[k] = cheb_next<T>(a, fc[(2 + k) * LW]);                      // filter.py:263-264
-                    b1[k] = (T)bar_update((double)fc[(4 + k) * LW], P.pa, (double)tn[k]);  // filter.py:265-266
-                }
-            }
-        }
-        // LAG 1: step i+1 at row j-1 consumes the T_i(j) just produced
-        if (LAG == 1 && s >= 1) step2(s, tn[0], tn[1]);
+    // ring positions of staged rows s+1 ("next") in both rings; element offsets of rows s-1, s, s+1
+    RingPos<FS> fn{0, 0};
+    RingPos<CS> cn{0, 0};
+    int fs_cur = 0, cs_cur = 0, cs_prev = 0;  // slots of rows s (both rings) and s-1 (coefficient ring)
+#pragma unroll CG2_UNROLL
+    for (int s = 0; s + 1 < nstage; ++s) {
+        fn.next();
+        cn.next();
+        const int f_nxt = fn.slot * FSLOT, c_nxt = cn.slot * CSLOT;
+        const int f_cur = fs_cur * FSLOT, c_cur = cs_cur * CSLOT, c_prev = cs_prev * CSLOT;
+        mbar_wait_a(fullF_a + 8u * (unsigned)fn.slot, fn.phase);
+        mbar_wait_a(fullC_a + 8u * (unsigned)cn.slot, cn.phase);
+        // ---- step i at row j = R0 + s (valid from s = 1 on: rows j0-1 .. j1)
+        const T* fnx = fcol + f_nxt;
+        const T* fc = fcol + f_cur;
+        T lap[2], x[2], tn[2], b1[2];
+        OP::row(S1, fnx[0], fnx[LW], ccol + c_nxt, ccol + c_cur, lap, x);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            if (LAG == 2) { xd[LAG - 1][k] = xd[0][k]; bd[LAG - 1][k] = bd[0][k]; tnd[k] = tn[k]; }
-            xd[0][k] = x[k];
-            bd[0][k] = b1[k];
+            const T a = -x[k] - cc * lap[k];                                   // filter.py:232-236
+            if (FIRST) {
+                tn[k] = a;
+                b1[k] = (T)bar_update(P.p0 * (double)x[k], P.pa, (double)a);   // filter.py:253-254
+            } else {
+                tn[k] = cheb_next<T>(a, fc[(2 + k) * LW]);                      // filter.py:263-264
+                b1[k] = (T)bar_update((double)fc[(4 + k) * LW], P.pa, (double)tn[k]);  // filter.py:265-266
+            }
+        }
+        // ---- step i+1 at row j-1: its "row j+1" is the T_i(j) just produced (valid from s = 3 on: rows j0 .. j1-1)
+        if (s >= 1) {
+            T lap2[2], x2[2];
+            OP::row(S2, tn[0], tn[1], ccol + c_cur, ccol + c_prev, lap2, x2);
+            if (s >= 3) {
+                if (emit) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const T a2 = -x2[k] - cc * lap2[k];
+                        const T t = cheb_next<T>(a2, xd[k]);
+                        if (!LAST) {
+                            *p1[k] = t;
+                            *p2[k] = x2[k];
+                        }
+                        *pb[k] = (T)bar_update((double)bd[k], P.pb, (double)t);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    pb[k] += P.bar[k].pitch;
+                    if (!LAST) { p1[k] += P.t1o[k].pitch; p2[k] += P.t2o[k].pitch; }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            xd[k] = x[k];
+            bd[k] = b1[k];
         }
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&emptyF[s % FS]);                       // field row s: u, v read last iteration, T_{i-2} / bar just now
-            if (s >= LAG) mbar_arrive(&emptyC[(s - LAG) % CS]);  // coefficient row s-LAG: step i+1 is done with it
+            mbar_arrive_a(emptyF_a + 8u * (unsigned)fs_cur);                // field row s: read for the last time just now
+            if (s >= 1) mbar_arrive_a(emptyC_a + 8u * (unsigned)cs_prev);   // coefficient row s-1: step i+1 is done with it
         }
+        cs_prev = cs_cur;
+        cs_cur = cn.slot;
+        fs_cur = fn.slot;
     }
 }
 #endif  // __CUDACC__

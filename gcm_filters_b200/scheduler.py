@@ -419,12 +419,13 @@ class PeerBandedFilter(BandedFilter):
 
 
 class FusedBandedFilter(BandedFilter):
-    """Latitude bands driven by the temporally blocked kernel: every rank keeps ``H = 4`` ghost rows per side,
-    runs up to four Chebyshev steps per launch (``gcmf_cheb_fused`` on a band plan) and exchanges the ghost
-    rows of ``T_{i+k-1}`` and ``T_{i+k-2}`` **once per block** instead of once per step (north_star item 3:
-    "per-step-block halo exchange").  Scalar FLUX / REGULAR5 operators on doubly periodic or tripolar grids (the
-    top band folds onto itself inside the kernel, the bottom band has no southern neighbour); every band must
-    be at least one tile high (32 rows) and ``nx`` a multiple of the vector width.
+    """Latitude bands driven by the temporally blocked kernels: every rank keeps ``H`` ghost rows per side, runs ``H``
+    Chebyshev steps per launch (``gcmf_cheb_fused`` on a band plan) and exchanges the ghost rows of ``T_{i+k-1}``
+    and ``T_{i+k-2}`` **once per block** instead of once per step (north_star item 3: "per-step-block halo
+    exchange").  Scalar FLUX / REGULAR5 operators (``H = 4``) on doubly periodic or tripolar grids (the top band
+    folds onto itself inside the kernel, the bottom band has no southern neighbour; every band at least one tile
+    = 32 rows high) and the vector operators (``H = 2``: the two-step row-streaming kernel; cfg5's 2160 x 4320
+    C-grid field on 8 GPUs is eight bands of 270 rows); ``nx`` a multiple of the vector width.
 
     ``exchange="nccl"``: pack, grouped NCCL send/recv, unpack.  ``exchange="peer"``: the ghosted arrays live in
     symmetric memory; after a device-side barrier every rank *pulls* its ghost rows straight out of its
@@ -446,18 +447,19 @@ class FusedBandedFilter(BandedFilter):
         gc.collect()
 
     def _fused_plan(self, np_dtype, ny, nx):
-        H = 4
+        H = 4 if self.lap.ncomp == 1 else 2  # steps per block = ghost rows per side (scalar tiles: 4, vector rows: 2)
         h, keep, j0, j1, flags = self._plan(np_dtype, ny, nx, halo=H)
         if self.lib.fused_max_steps(h) < H:
-            raise ValueError("this operator / band size has no fused kernel (band >= 32 rows, nx >= one tile, "
-                             "nx a multiple of the 16-byte vector width)")
+            raise ValueError("this operator / band size has no fused kernel (scalar: band >= 32 rows, nx >= one tile; "
+                             "vector: nx >= 232; nx a multiple of the 16-byte vector width)")
         return h, j0, j1, flags, H
 
     def stage(self, *fields):
         import torch
 
         lap = self.lap
-        assert lap.ncomp == 1 and len(fields) == 1, "scalar operators only"
+        ncomp = lap.ncomp
+        assert len(fields) == ncomp, f"this operator filters {ncomp} field(s) at a time"
         f0 = np.asarray(fields[0])
         ny, nx = f0.shape[-2:]
         np_dtype = lap.compute_dtype(f0.dtype if f0.dtype.kind == "f" else np.float64)
@@ -472,7 +474,7 @@ class FusedBandedFilter(BandedFilter):
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
 
-            n_arrays, slab = 6, nb * rows * nx
+            n_arrays, slab = 6, ncomp * nb * rows * nx
             if self._symm is None or self._symm[0] != (tdt, slab):
                 buf = symm_mem.empty(n_arrays * slab, dtype=tdt, device=self.device)
                 hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
@@ -484,16 +486,17 @@ class FusedBandedFilter(BandedFilter):
             buf.zero_()
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)
-            arrays = [buf[k * slab:(k + 1) * slab].view(1, nb, rows, nx) for k in range(n_arrays)]
+            arrays = [buf[k * slab:(k + 1) * slab].view(ncomp, nb, rows, nx) for k in range(n_arrays)]
             north, south = (self.rank + 1) % self.world, (self.rank - 1) % self.world
             peers = dict(hdl=hdl, nyl_south=bands[south][1] - bands[south][0],
-                         north=[hdl.get_buffer(north, (1, nb, rows, nx), tdt, k * slab) for k in range(n_arrays)],
-                         south=[hdl.get_buffer(south, (1, nb, rows, nx), tdt, k * slab) for k in range(n_arrays)])
+                         north=[hdl.get_buffer(north, (ncomp, nb, rows, nx), tdt, k * slab) for k in range(n_arrays)],
+                         south=[hdl.get_buffer(south, (ncomp, nb, rows, nx), tdt, k * slab) for k in range(n_arrays)])
         else:
-            arrays = [torch.zeros((1, nb, rows, nx), dtype=tdt, device=self.device) for _ in range(6)]
-        X0 = torch.as_tensor(np.ascontiguousarray(f0.reshape((nb, ny, nx))[:, j0:j1])).to(device=self.device, dtype=tdt)
-        return dict(h=h, flags=flags, j0=j0, j1=j1, nyl=nyl, nb=nb, nx=nx, ncomp=1, H=H, rows=rows, X0=X0, arrays=arrays,
-                    peers=peers, bar=torch.empty((1, nb, nyl, nx), dtype=tdt, device=self.device),
+            arrays = [torch.zeros((ncomp, nb, rows, nx), dtype=tdt, device=self.device) for _ in range(6)]
+        X0 = torch.stack([torch.as_tensor(np.ascontiguousarray(np.asarray(f).reshape((nb, ny, nx))[:, j0:j1]))
+                          for f in fields]).to(device=self.device, dtype=tdt)
+        return dict(h=h, flags=flags, j0=j0, j1=j1, nyl=nyl, nb=nb, nx=nx, ncomp=ncomp, H=H, rows=rows, X0=X0,
+                    arrays=arrays, peers=peers, bar=torch.empty((ncomp, nb, nyl, nx), dtype=tdt, device=self.device),
                     batch_shape=f0.shape[:-2])
 
     def _exchange_ghosts(self, st, idxs):
@@ -524,13 +527,15 @@ class FusedBandedFilter(BandedFilter):
         A, bar = st["arrays"], st["bar"]
         es = A[0].element_size()
 
-        def inner(k):  # the owned rows start H rows into the ghosted array
-            return [(A[k][0].data_ptr() + H * nx * es, nx, rows * nx)]
+        ncomp = st["ncomp"]
 
-        plain = [(bar[0].data_ptr(), nx, nyl * nx)]
+        def inner(k):  # the owned rows start H rows into the ghosted array
+            return [(A[k][c].data_ptr() + H * nx * es, nx, rows * nx) for c in range(ncomp)]
+
+        plain = [(bar[c].data_ptr(), nx, nyl * nx) for c in range(ncomp)]
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
         x = 0
-        A[0][0, :, H:H + nyl].copy_(st["X0"])
+        A[0][:, :, H:H + nyl].copy_(st["X0"])
         if flags & _AREA_FLAG:  # x = f * area on the owned rows (kernels.py:100-101), then its ghosts
             lib.prepare(h, nb, inner(0), inner(1), stream)
             x = 1

@@ -154,8 +154,13 @@ int gcmf_cheb_step(gcmf_plan *plan, int64_t nb, int32_t step, const gcmf_field *
  * gcmf_cheb_fused: recurrence steps step .. step+k-1 (1 <= step, step+k-1 <= n_steps) in one launch:
  *   reads T_{step-1} (`t1_in`; the prepared field when step == 1) and T_{step-2} (`t2_in`, ignored when
  *   step == 1), writes T_{step+k-1} (`t1_out`) and T_{step+k-2} (`t2_out`) unless the block reaches
- *   n_steps, and updates `bar` (initialised by step 1, finalized by step n_steps).  Scalar operators
- *   only; outputs must not alias inputs (neighbouring tiles read the inputs' halos). */
+ *   n_steps, and updates `bar` (initialised by step 1, finalized by step n_steps).  Outputs must not alias
+ *   inputs (neighbouring tiles read the inputs' halos).  Scalar operators fuse 1..4 steps (tiles + 4-cell
+ *   halos); the vector operators (each field argument is an array of two gcmf_field: u, v) fuse exactly
+ *   k = 2 steps per launch (rows streamed once for both steps; k = 1 is accepted for the trailing step of
+ *   an odd n_steps and runs the one-step kernel).  On a band plan (GCMF_FLAG_WRAP_Y clear) the caller
+ *   keeps gcmf_fused_max_steps() ghost rows of the fields and of every plane on either side of the band
+ *   and refreshes those of t1_out / t2_out after every block. */
 int gcmf_fused_max_steps(const gcmf_plan *plan);
 int gcmf_plan_set_steps_per_block(gcmf_plan *plan, int32_t k);
 int gcmf_cheb_fused(gcmf_plan *plan, int64_t nb, int32_t step, int32_t k, const gcmf_field *t1_in,

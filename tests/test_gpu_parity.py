@@ -544,3 +544,30 @@ def test_vector_two_step_kernel_is_bit_identical_to_one_step(g, shape, nb, n_ste
             engine.set_steps_per_block(0)
         assert fu.dtype == dtype
         assert np.array_equal(fu, pu, equal_nan=True) and np.array_equal(fv, pv, equal_nan=True), rows
+
+
+@pytest.mark.parametrize("g,shape", [("VECTOR_C_GRID", (96, 488)), ("VECTOR_B_GRID", (64, 232)), ("IRREGULAR_WITH_LAND", (96, 264))])
+def test_fused_banded_single_rank_is_its_own_neighbour(g, shape):
+    """FusedBandedFilter with one rank (the band wraps onto itself: ghost rows refreshed by local copies once per block):
+    the temporally blocked kernels on a BAND plan -- physical ghost rows instead of the periodic wrap, 2 per side for
+    the two-step vector kernel, 4 for the scalar tiles -- on one GPU, against the whole-grid one-step kernels, bit for
+    bit.  Odd and even step counts (the vector path ends an odd count with a one-step LAST launch)."""
+    from gcm_filters_b200 import engine
+    from gcm_filters_b200.scheduler import FusedBandedFilter
+    fields, gv = fixtures.fixture(g, shape)
+    fields = tuple(np.stack([f, 1.0 - f * f]) for f in fields)
+    for scale in (6.0, 7.0):
+        fa = vec_args(g, gv, dict(filter_scale=scale, dx_min=1.0))
+        flt = make_filter(g, gv, **fa)
+        try:
+            engine.set_steps_per_block(1)
+            single = run_filter(flt, fields)
+        finally:
+            engine.set_steps_per_block(0)
+        fbf = FusedBandedFilter(flt, 0, 1)
+        for _ in range(2):
+            outs, (j0, j1) = fbf.apply(*fields)
+        fbf.close()
+        assert (j0, j1) == (0, shape[0])
+        for o, s in zip(outs, single):
+            assert np.array_equal(o, s, equal_nan=True), (g, scale, flt.n_steps)
