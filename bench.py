@@ -601,15 +601,15 @@ def free_device(ctx):
 def banded_secondary(ctx, args, fused=False):
     """cfg5 (VECTOR_C_GRID 2160 x 4320) as latitude bands, one per GPU (strong scaling of one 2-D field).  fused=False:
     one-step kernels that store their border rows straight into the neighbours' peer memory (PeerBandedFilter);
-    fused=True: the two-step kernel on bands with two ghost rows per side, pulled from the neighbours' peer memory once
-    per two-step block (FusedBandedFilter, exchange="peer")."""
+    fused=True: the two-step kernel on bands with two ghost rows per side, which the kernel itself stores into the
+    neighbours' peer memory (FusedBandedFilter, exchange="push")."""
     from gcm_filters_b200 import _cabi
     from gcm_filters_b200.scheduler import FusedBandedFilter, PeerBandedFilter
 
     torch = ctx.torch
     cfg = build_workload("cfg5")
     flt = make_filter(cfg)
-    bf = FusedBandedFilter(flt, ctx.rank, ctx.world, exchange="peer") if fused else PeerBandedFilter(flt, ctx.rank, ctx.world)
+    bf = FusedBandedFilter(flt, ctx.rank, ctx.world, exchange="push") if fused else PeerBandedFilter(flt, ctx.rank, ctx.world)
     st = bf.stage(*cfg["fields"])
     lib = _cabi.get_library()
     f0 = cfg["fields"][0]
@@ -634,7 +634,8 @@ def banded_secondary(ctx, args, fused=False):
     return {"workload": config_of(cfg, n_steps, (ny, nx), f0.dtype)["workload"], "value": value,
             "ms_per_step": ms / steps, "n_steps": n_steps, "whole_call_frac": b_alg * value / ctx.world / 1e9 / peak,
             "sharding": (f"{ctx.world} latitude band(s); two Chebyshev steps per launch on bands with 2 ghost rows per side, "
-                         f"pulled from the neighbours' peer memory over NVLink once per block (no NCCL on the data path)"
+                         f"stored by the kernel into the neighbours' peer memory over NVLink as it emits them, "
+                         f"flag-synchronised (one launch per two steps, no NCCL on the data path)"
                          if fused else
                          f"{ctx.world} latitude band(s); ghost rows stored by the step kernels into the neighbours' peer "
                          f"memory over NVLink, flag-synchronised (no NCCL on the data path)")}
@@ -716,7 +717,7 @@ def banded_arm(args):
     flt = make_filter(cfg)
     n_steps = int(flt.n_steps)
     if args.fused:
-        bf = FusedBandedFilter(flt, rank, world, exchange="peer" if args.peer else "nccl")
+        bf = FusedBandedFilter(flt, rank, world, exchange="push" if args.push else ("peer" if args.peer else "nccl"))
     else:
         bf = (PeerBandedFilter if args.peer else BandedFilter)(flt, rank, world)
     st = bf.stage(*cfg["fields"])
@@ -773,7 +774,9 @@ def banded_arm(args):
         "dtype": "f64" if w == 8 else "f32", "data": DATA,
         "config": dict(config_of(cfg, n_steps, f0.shape, f0.dtype),
                        sharding=f"{world} latitude band(s), " +
-                       (f"{H} ghost rows, fused {H}-step blocks, ghost rows pulled from peer memory once per block"
+                       (f"{H} ghost rows, fused {H}-step blocks, ghost rows stored by the kernel into the neighbours' peer memory "
+                        f"(NVLink), flag-synchronised" if args.fused and args.push else
+                        f"{H} ghost rows, fused {H}-step blocks, ghost rows pulled from peer memory once per block"
                         if args.fused and args.peer else
                         f"{H} ghost rows, fused {H}-step blocks, one NCCL exchange per block" if args.fused else
                         "ghost rows stored by the step kernels into the neighbours' peer memory (NVLink), flag-synchronised"
@@ -878,6 +881,8 @@ def main():
                     help="with --banded: temporally blocked kernel on the bands, one ghost exchange per 4-step block")
     ap.add_argument("--peer", action="store_true",
                     help="with --banded: ghost rows pushed by the step kernels through peer memory instead of NCCL")
+    ap.add_argument("--push", action="store_true",
+                    help="with --banded --fused (vector operators): ghost-row exchange fused into the two-step kernel")
     ap.add_argument("--banded", action="store_true",
                     help="latitude-band domain decomposition (strong scaling of one 2-D field; cfg5)")
     args = ap.parse_args()

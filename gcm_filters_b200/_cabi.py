@@ -19,7 +19,7 @@ EXPORTS = [
     "gcmf_version", "gcmf_sm_arch", "gcmf_last_error", "gcmf_plan_create", "gcmf_plan_destroy",
     "gcmf_plan_set_plane", "gcmf_plan_set_filter", "gcmf_workspace_bytes", "gcmf_laplacian", "gcmf_filter",
     "gcmf_cheb_step", "gcmf_prepare", "gcmf_launch_count", "gcmf_fused_max_steps", "gcmf_plan_set_steps_per_block",
-    "gcmf_cheb_fused", "gcmf_cheb_step_halo", "gcmf_halo_push", "gcmf_finalize",
+    "gcmf_cheb_fused", "gcmf_cheb_step_halo", "gcmf_halo_push", "gcmf_finalize", "gcmf_cheb_fused_halo",
 ]
 
 
@@ -83,6 +83,8 @@ class Library:
         lib.gcmf_cheb_step_halo.restype = ctypes.c_int
         lib.gcmf_halo_push.argtypes = [vp, i64, fp, hp, vp]
         lib.gcmf_halo_push.restype = ctypes.c_int
+        lib.gcmf_cheb_fused_halo.argtypes = [vp, i64, i32, i32, fp, fp, fp, fp, fp, hp, hp, vp]
+        lib.gcmf_cheb_fused_halo.restype = ctypes.c_int
         for name in ("gcmf_plan_create", "gcmf_plan_destroy", "gcmf_plan_set_plane", "gcmf_plan_set_filter",
                      "gcmf_workspace_bytes", "gcmf_laplacian", "gcmf_prepare", "gcmf_filter", "gcmf_cheb_step"):
             getattr(lib, name).restype = ctypes.c_int
@@ -117,8 +119,8 @@ class Library:
     @staticmethod
     def fields(specs):
         """specs: list of (ptr, pitch, bstride) -> ctypes array of gcmf_field (or None)."""
-        if specs is None:
-            return None
+        if specs is None or isinstance(specs, ctypes.Array):  # already converted (callers on a launch-bound path cache them)
+            return specs
         arr = (Field * len(specs))()
         for k, (ptr, pitch, bstride) in enumerate(specs):
             arr[k] = Field(ptr, pitch, bstride)
@@ -154,6 +156,11 @@ class Library:
     def cheb_step_halo(self, h, nb, step, t1, t2, t0, bar, halo, stream=0):
         self.check(self.lib.gcmf_cheb_step_halo(h, nb, step, self.fields(t1), self.fields(t2), self.fields(t0),
                                                 self.fields(bar), ctypes.byref(halo), ctypes.c_void_p(stream)))
+
+    def cheb_fused_halo(self, h, nb, step, k, t1, t2, t1o, t2o, bar, halo1, halo2, stream=0):
+        self.check(self.lib.gcmf_cheb_fused_halo(h, nb, step, k, self.fields(t1), self.fields(t2), self.fields(t1o),
+                                                 self.fields(t2o), self.fields(bar), ctypes.byref(halo1),
+                                                 ctypes.byref(halo2), ctypes.c_void_p(stream)))
 
     def halo_push(self, h, nb, field, halo, stream=0):
         self.check(self.lib.gcmf_halo_push(h, nb, self.fields(field), ctypes.byref(halo), ctypes.c_void_p(stream)))

@@ -29,7 +29,6 @@
 #include "gcmf_fused.cuh"
 #ifndef GCMF_HOSTEMU
 #include "gcmf_march.cuh"
-#include "gcmf_vec2.cuh"
 #endif
 
 using namespace gcmf;
@@ -392,6 +391,7 @@ __global__ void __launch_bounds__(32 * CG_WARPS, GCMF_CGM_MINBLOCKS) cgrid_march
 }
 
 #undef LDRO
+#include "gcmf_vec2.cuh"  // two-step vector kernel: uses halo_wait / halo_signal / halo_band_order from above
 // VECTOR_C, TMA-pipelined row streaming (the default for 16-byte aligned arrays).  ncu of the marching kernel above:
 // 89 % of the warp stalls are long_scoreboard, DRAM at 54 % -- its loads live in registers, so the bytes in flight are
 // capped by the register file (16 warps x 24 loads).  Here the loads live in shared memory instead: a producer lane
@@ -1340,14 +1340,15 @@ static bool cg2_eligible(const gcmf_plan* p) {
 }
 
 #ifndef GCMF_HOSTEMU
-template <typename T, template <typename, int> class OPT, int EDGE>
+template <typename T, template <typename, int> class OPT, int EDGE, bool HALO>
 static int launch_cg2_t(const gcmf_plan* pl, const Cg2Params<T>& P, cudaStream_t st) {
     using G = Vec2Geom<T, OPT<T, 1>::NC>;
     static bool attr_done[64] = {false};
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(vec2_kernel<T, OPT, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes()));
+        CUDA_TRY(cudaFuncSetAttribute(vec2_kernel<T, OPT, EDGE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)G::smem_bytes()));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const int ny = P.g.ny;
@@ -1363,6 +1364,8 @@ static int launch_cg2_t(const gcmf_plan* pl, const Cg2Params<T>& P, cudaStream_t
         double best = 1e300;
         const int lo = ny < 12 ? ny : 12, hi = ny < 64 ? ny : 64;
         for (int cand = lo; cand <= hi; ++cand) {
+            // with the exchange fused in, the first and the last row-band own the two border rows they push
+            if (HALO && (cand < 2 || ny % cand == 1)) continue;
             const int64_t ncta = ctas_x * P.nb * ((ny + cand - 1) / cand);
             const int64_t rounds = (ncta + pl->sm_count - 1) / pl->sm_count;
             const double cost = (double)rounds * (cand + 6);
@@ -1372,32 +1375,40 @@ static int launch_cg2_t(const gcmf_plan* pl, const Cg2Params<T>& P, cudaStream_t
             }
         }
     }
-    if (ry > ny) ry = ny;
+    if (ry <= 0 || ry > ny) ry = ny;
+    if (HALO)
+        while (ry < ny && (ry < 2 || ny % ry == 1)) ++ry;
     const int64_t nbands = (ny + ry - 1) / ry;
     const int64_t nblk = ctas_x * P.nb * nbands;
     if (nblk > 0x7fffffffLL) return gcmf_set_error(GCMF_EINVAL, "grid too large (%lld blocks)", (long long)nblk);
-    vec2_kernel<T, OPT, EDGE><<<(unsigned)nblk, G::NTHREADS, G::smem_bytes(), st>>>(P, (unsigned)ctas_x, ry);
+    vec2_kernel<T, OPT, EDGE, HALO><<<(unsigned)nblk, G::NTHREADS, G::smem_bytes(), st>>>(P, (unsigned)ctas_x, ry);
     gcmf_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return GCMF_OK;
 }
+template <typename T, template <typename, int> class OPT, bool HALO>
+static int launch_cg2_h(const gcmf_plan* pl, const Cg2Params<T>& P, bool first, bool last, cudaStream_t st) {
+    switch ((first ? 1 : 0) | (last ? 2 : 0)) {
+        case 0: return launch_cg2_t<T, OPT, 0, HALO>(pl, P, st);
+        case 1: return launch_cg2_t<T, OPT, 1, HALO>(pl, P, st);
+        case 2: return launch_cg2_t<T, OPT, 2, HALO>(pl, P, st);
+    }
+    return launch_cg2_t<T, OPT, 3, HALO>(pl, P, st);
+}
 template <typename T, template <typename, int> class OPT>
 static int launch_cg2(const gcmf_plan* pl, const Cg2Params<T>& P, bool first, bool last, cudaStream_t st) {
-    switch ((first ? 1 : 0) | (last ? 2 : 0)) {
-        case 0: return launch_cg2_t<T, OPT, 0>(pl, P, st);
-        case 1: return launch_cg2_t<T, OPT, 1>(pl, P, st);
-        case 2: return launch_cg2_t<T, OPT, 2>(pl, P, st);
-    }
-    return launch_cg2_t<T, OPT, 3>(pl, P, st);
+    if (P.halo[0].enabled) return launch_cg2_h<T, OPT, true>(pl, P, first, last, st);
+    return launch_cg2_h<T, OPT, false>(pl, P, first, last, st);
 }
 #endif
 
 // steps step0 and step0+1 of a vector plan in one launch
 template <typename T>
 static int run_cg2_t(const gcmf_plan* pl, int64_t nb, int step0, const gcmf_field* t1, const gcmf_field* t2,
-                     const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st) {
+                     const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st,
+                     const gcmf_halo* halo1 = nullptr, const gcmf_halo* halo2 = nullptr) {
 #ifdef GCMF_HOSTEMU
-    (void)pl; (void)nb; (void)step0; (void)t1; (void)t2; (void)t1o; (void)t2o; (void)bar; (void)st;
+    (void)pl; (void)nb; (void)step0; (void)t1; (void)t2; (void)t1o; (void)t2o; (void)bar; (void)st; (void)halo1; (void)halo2;
     return gcmf_set_error(GCMF_EINVAL, "the two-step C-grid kernel is device-only");
 #else
     using G = Cg2Geom<T>;
@@ -1430,6 +1441,10 @@ static int run_cg2_t(const gcmf_plan* pl, int64_t nb, int step0, const gcmf_fiel
             P.t2o[k] = FieldRef<T>{(T*)t2o[k].ptr, t2o[k].pitch, t2o[k].bstride};
         }
         P.bar[k] = FieldRef<T>{(T*)bar[k].ptr, bar[k].pitch, bar[k].bstride};
+    }
+    if (halo1) {
+        P.halo[0] = make_halo<T>(halo1);
+        P.halo[1] = make_halo<T>(halo2 ? halo2 : halo1);
     }
     P.c = pl->c;
     P.p0 = pl->p[0];
@@ -1565,6 +1580,35 @@ extern "C" int gcmf_cheb_fused(gcmf_plan* p, int64_t nb, int32_t step, int32_t k
     if (p->desc.dtype == GCMF_F64)
         return run_fused_t<double>(p, nb, step, k, t1_in, t2_in, t1_out, t2_out, bar, (cudaStream_t)stream);
     return run_fused_t<float>(p, nb, step, k, t1_in, t2_in, t1_out, t2_out, bar, (cudaStream_t)stream);
+}
+
+// gcmf_cheb_fused on a latitude band with the ghost-row exchange fused into the kernel (vector operators, k = 2)
+extern "C" int gcmf_cheb_fused_halo(gcmf_plan* p, int64_t nb, int32_t step, int32_t k, const gcmf_field* t1_in,
+                                    const gcmf_field* t2_in, const gcmf_field* t1_out, const gcmf_field* t2_out,
+                                    const gcmf_field* bar, const gcmf_halo* halo_t1, const gcmf_halo* halo_t2, void* stream) {
+    if (!p || nb < 1 || !halo_t1 || !halo_t2) return gcmf_set_error(GCMF_EINVAL, "bad argument");
+    if (p->desc.flags & GCMF_FLAG_WRAP_Y) return gcmf_set_error(GCMF_EINVAL, "halo exchange needs a band plan (no GCMF_FLAG_WRAP_Y)");
+    if (p->n_steps < 2) return gcmf_set_error(GCMF_ESTATE, "gcmf_plan_set_filter has not been called");
+    if (!cg2_eligible(p))
+        return gcmf_set_error(GCMF_EINVAL, "gcmf_cheb_fused_halo: vector plans with a two-step kernel only (see gcmf_fused_max_steps)");
+    if (k != 2 || step < 1 || step + 1 > p->n_steps)
+        return gcmf_set_error(GCMF_EINVAL, "gcmf_cheb_fused_halo: k must be 2 and steps %d..%d inside 1..%d", step, step + 1, p->n_steps);
+    if (p->desc.ny < 4) return gcmf_set_error(GCMF_EINVAL, "gcmf_cheb_fused_halo: a band needs at least 4 rows");
+    if (halo_t1->wait_north != halo_t2->wait_north || halo_t1->wait_south != halo_t2->wait_south ||
+        halo_t1->north_bstride != halo_t2->north_bstride || halo_t1->south_bstride != halo_t2->south_bstride)
+        return gcmf_set_error(GCMF_EINVAL, "gcmf_cheb_fused_halo: the two halos must share flags and batch strides");
+    TRY(check_planes(p));
+    TRY(check_fields(p, t1_in, "t1_in"));
+    if (step > 1) TRY(check_fields(p, t2_in, "t2_in"));
+    if (step + 1 < p->n_steps) {
+        TRY(check_fields(p, t1_out, "t1_out"));
+        TRY(check_fields(p, t2_out, "t2_out"));
+    }
+    TRY(check_fields(p, bar, "bar"));
+    CUDA_TRY(cudaSetDevice(p->desc.device));
+    if (p->desc.dtype == GCMF_F64)
+        return run_cg2_t<double>(p, nb, step, t1_in, t2_in, t1_out, t2_out, bar, (cudaStream_t)stream, halo_t1, halo_t2);
+    return run_cg2_t<float>(p, nb, step, t1_in, t2_in, t1_out, t2_out, bar, (cudaStream_t)stream, halo_t1, halo_t2);
 }
 
 extern "C" int gcmf_filter(gcmf_plan* p, int64_t nb, const gcmf_field* in, const gcmf_field* out, void* workspace,

@@ -89,6 +89,9 @@ template <typename T> struct Cg2Params {
     int64_t nb;
     int32_t cpw;               // output columns per warp, <= CG2_COLS (strips of equal width)
     int32_t lw;                // staged columns per row: CG2_WARPS*cpw + 2*HALO
+    // latitude bands with the ghost-row exchange fused in (gcmf_cheb_fused_halo): where the first / last two rows of
+    // t1o (halo[0]) and t2o (halo[1]) go in the neighbouring GPUs' arrays; the flags and counters of halo[0] are used
+    HaloRef<T> halo[2];
 };
 
 #ifdef __CUDACC__
@@ -210,7 +213,11 @@ template <int N> struct RingPos {
 // EDGE bit 1: the block ends at step n_steps (no T is stored).
 // Warps 0..CG2_WARPS-1 consume; warp CG2_WARPS streams the field ring, warp CG2_WARPS+1 the coefficient ring (each at
 // its own pace: the field rows are released one iteration earlier than the coefficient rows).
-template <typename T, template <typename, int> class OPT, int EDGE>
+// HALO (latitude band): border row-bands wait for the neighbours' flags before touching the ghost rows, store their
+// first / last two rows of T_{i+1} and T_i straight into the neighbours' ghost rows (peer memory, NVLink) as they emit
+// them, and the last border CTA to finish raises the neighbours' flags -- halo_wait / halo_signal of gcmf.cu, the
+// protocol of gcmf_cheb_step_halo with two rows and two arrays per block.  Border bands are scheduled first.
+template <typename T, template <typename, int> class OPT, int EDGE, bool HALO>
 __global__ void __launch_bounds__(32 * (CG2_WARPS + 2), 1) vec2_kernel(const __grid_constant__ Cg2Params<T> P, unsigned ctas_x, int ry) {
     using OP = OPT<T, Vec2Geom<T, 14>::LW>;
     using G = Vec2Geom<T, OP::NC>;
@@ -230,16 +237,18 @@ __global__ void __launch_bounds__(32 * (CG2_WARPS + 2), 1) vec2_kernel(const __g
     bid /= ctas_x;
     const unsigned nbu = (unsigned)P.nb;
     const int b = (int)(bid % nbu);
-    const int band = (int)(bid / nbu);
     const int ny = P.g.ny, nx = P.g.nx;
+    const int band = HALO ? halo_band_order((int)(bid / nbu), (ny + ry - 1) / ry) : (int)(bid / nbu);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j0 = band * ry, j1 = j0 + ry < ny ? j0 + ry : ny;
+    const bool bottom = j0 == 0, top = j1 >= ny;
     if (threadIdx.x == 0) {
         for (int s = 0; s < FS; ++s) { mbar_init(&fullF[s], 1); mbar_init(&emptyF[s], CG2_WARPS); }
         for (int s = 0; s < CS; ++s) { mbar_init(&fullC[s], 1); mbar_init(&emptyC[s], CG2_WARPS); }
         fence_mbar_init();
     }
     __syncthreads();
+    if (HALO) halo_wait<T>(P.halo[0], bottom, top);
     // staged rows R0 .. j1+1: step i+1 emits rows j0 .. j1-1, needs T_i on j0-1 .. j1, which needs the input on j0-2 .. j1+1
     const int R0 = j0 - 2;
     const int nstage = (j1 - j0) + 4;
@@ -287,6 +296,7 @@ __global__ void __launch_bounds__(32 * (CG2_WARPS + 2), 1) vec2_kernel(const __g
         const int lw = P.lw;
         const int n1 = (nx - gx) < lw ? (nx - gx) : lw;
         const unsigned rowb = (unsigned)(lw * sizeof(T));
+        if (HALO) asm volatile("fence.proxy.async;" ::: "memory");  // ghost rows written by the peers, acquired above
         int slot = 0;
         unsigned phase = 0;  // parity of the "empty" phase the producer waits for (second lap: 0, third: 1, ...)
         for (int q = 0; q < nstage; ++q) {
@@ -310,9 +320,7 @@ __global__ void __launch_bounds__(32 * (CG2_WARPS + 2), 1) vec2_kernel(const __g
                 if (q >= nslot) phase ^= 1u;
             }
         }
-        return;
-    }
-
+    } else {
     // ---- consumers
     const int lc = G::HALO - 2 + warp * P.cpw + lane;              // this lane's column in a staged row
     const int i = cx * strip + warp * P.cpw + lane - 2;            // global column (unwrapped; < 0 or >= nx: never emitted)
@@ -382,6 +390,19 @@ __global__ void __launch_bounds__(32 * (CG2_WARPS + 2), 1) vec2_kernel(const __g
                         if (!LAST) {
                             *p1[k] = t;
                             *p2[k] = x2[k];
+                            if (HALO) {  // rows 0, 1 -> the south neighbour's north ghost rows; ny-2, ny-1 -> the north neighbour's south ghosts
+                                const int rj = j0 + s - 3;
+                                if (rj < 2 && P.halo[0].south[k]) {
+                                    const int64_t o = (int64_t)b * P.halo[0].sbs + (int64_t)rj * P.t1o[k].pitch + i;
+                                    P.halo[0].south[k][o] = t;
+                                    P.halo[1].south[k][o] = x2[k];
+                                }
+                                if (rj >= ny - 2 && P.halo[0].north[k]) {
+                                    const int64_t o = (int64_t)b * P.halo[0].nbs + (int64_t)(rj - (ny - 2)) * P.t1o[k].pitch + i;
+                                    P.halo[0].north[k][o] = t;
+                                    P.halo[1].north[k][o] = x2[k];
+                                }
+                            }
                         }
                         *pb[k] = (T)bar_update((double)bd[k], P.pb, (double)t);
                     }
@@ -407,6 +428,8 @@ __global__ void __launch_bounds__(32 * (CG2_WARPS + 2), 1) vec2_kernel(const __g
         cs_cur = cn.slot;
         fs_cur = fn.slot;
     }
+    }  // consumers
+    if (HALO) halo_signal<T>(P.halo[0], bottom, top, ctas_x * nbu);
 }
 #endif  // __CUDACC__
 

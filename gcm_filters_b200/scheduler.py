@@ -431,14 +431,24 @@ class FusedBandedFilter(BandedFilter):
     symmetric memory; after a device-side barrier every rank *pulls* its ghost rows straight out of its
     neighbours' arrays over NVLink (four strided copies per block, no NCCL, no packing).  Two buffer pairs
     ping-pong between blocks, so one barrier per block also covers the write-after-read hazards.
+    ``exchange="push"`` (vector operators): the exchange is **fused into the two-step kernel**
+    (``gcmf_cheb_fused_halo``): the border row-bands store their two first / last rows of ``T_{i+1}`` and ``T_i``
+    straight into the neighbours' ghost rows as they emit them and the last border CTA raises a flag in the
+    neighbour's memory; the next block over there spins on that flag only in the CTAs that touch ghost rows.  One
+    launch per two Chebyshev steps and rank, no NCCL call, no copy kernels, no host synchronisation; only the ghost
+    rows of the input field are pulled once per call.  With one rank the band is its own neighbour (ordinary device
+    memory): the same kernels and protocol on a single GPU.
     """
 
     def __init__(self, flt, rank, world, group=None, library=None, device=None, exchange="nccl"):
         super().__init__(flt, rank, world, group=group, library=library, device=device)
-        if exchange not in ("nccl", "peer"):
-            raise ValueError("exchange must be 'nccl' or 'peer'")
-        self.exchange = exchange if self.world > 1 else "nccl"
+        if exchange not in ("nccl", "peer", "push"):
+            raise ValueError("exchange must be 'nccl', 'peer' or 'push'")
+        if exchange == "push" and self.lap.ncomp != 2:
+            raise ValueError("exchange='push' is implemented for the vector operators (two-step kernel)")
+        self.exchange = exchange if (self.world > 1 or exchange == "push") else "nccl"
         self._symm = None
+        self._epoch = 0
 
     def close(self):
         import gc
@@ -470,13 +480,21 @@ class FusedBandedFilter(BandedFilter):
         bands = band_rows(ny, self.world)
         rows = max(b - a for a, b in bands) + 2 * H  # common allocation so that every rank has the same layout
         peers = None
-        if self.exchange == "peer":
+        push = None
+        n_flag = 64  # elements reserved behind the arrays for the flag / counter words of exchange="push"
+        if self.exchange == "push" and self.world == 1:  # the band is its own neighbour: ordinary device memory
+            n_arrays, slab = 6, ncomp * nb * rows * nx
+            buf = torch.zeros(n_arrays * slab + n_flag, dtype=tdt, device=self.device)
+            arrays = [buf[k * slab:(k + 1) * slab].view(ncomp, nb, rows, nx) for k in range(n_arrays)]
+            push = dict(bases=[buf.data_ptr()], slab=slab, buf=buf, nyl_south=nyl)
+            self._epoch = 0
+        elif self.exchange in ("peer", "push"):
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
 
             n_arrays, slab = 6, ncomp * nb * rows * nx
             if self._symm is None or self._symm[0] != (tdt, slab):
-                buf = symm_mem.empty(n_arrays * slab, dtype=tdt, device=self.device)
+                buf = symm_mem.empty(n_arrays * slab + n_flag, dtype=tdt, device=self.device)
                 hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
                 self._symm = ((tdt, slab), buf, hdl)
             _, buf, hdl = self._symm
@@ -491,13 +509,45 @@ class FusedBandedFilter(BandedFilter):
             peers = dict(hdl=hdl, nyl_south=bands[south][1] - bands[south][0],
                          north=[hdl.get_buffer(north, (ncomp, nb, rows, nx), tdt, k * slab) for k in range(n_arrays)],
                          south=[hdl.get_buffer(south, (ncomp, nb, rows, nx), tdt, k * slab) for k in range(n_arrays)])
+            if self.exchange == "push":  # flags were cleared with the buffer, between two barriers: restart the epochs
+                push = dict(bases=[int(p) for p in hdl.buffer_ptrs], slab=slab, buf=buf,
+                            nyl_south=bands[south][1] - bands[south][0])
+                self._epoch = 0
         else:
             arrays = [torch.zeros((ncomp, nb, rows, nx), dtype=tdt, device=self.device) for _ in range(6)]
         X0 = torch.stack([torch.as_tensor(np.ascontiguousarray(np.asarray(f).reshape((nb, ny, nx))[:, j0:j1]))
                           for f in fields]).to(device=self.device, dtype=tdt)
         return dict(h=h, flags=flags, j0=j0, j1=j1, nyl=nyl, nb=nb, nx=nx, ncomp=ncomp, H=H, rows=rows, X0=X0,
-                    arrays=arrays, peers=peers, bar=torch.empty((ncomp, nb, nyl, nx), dtype=tdt, device=self.device),
-                    batch_shape=f0.shape[:-2])
+                    arrays=arrays, peers=peers, push=push,
+                    bar=torch.empty((ncomp, nb, nyl, nx), dtype=tdt, device=self.device), batch_shape=f0.shape[:-2])
+
+    def _push_halo(self, st, which, wait_value, signal_value, wait=True, push=True):
+        """gcmf_halo describing where the border rows of array `which` go in the neighbours' copies of that array (and
+        the flag words behind the arrays: [0] raised by the south neighbour, [1] by the north one, [2..3] counters)."""
+        ps = st["push"]
+        nx, rows, nb, ncomp, H = st["nx"], st["rows"], st["nb"], st["ncomp"], st["H"]
+        es = st["arrays"][0].element_size()
+        local = self.world == 1
+        me = ps["bases"][0 if local else self.rank]
+        north = ps["bases"][0 if local else (self.rank + 1) % self.world]
+        south = ps["bases"][0 if local else (self.rank - 1) % self.world]
+        flag_off = 6 * ps["slab"] * es
+        comp = nb * rows * nx * es  # bytes of one component of a ghosted array
+        hl = _cabi.Halo()
+        hl.north_bstride = hl.south_bstride = rows * nx
+        hl.counters = me + flag_off + 8
+        hl.wait_value, hl.signal_value = wait_value & 0xFFFFFFFF, signal_value & 0xFFFFFFFF
+        arr = which * ps["slab"] * es
+        for k in range(ncomp):
+            if push:  # my rows ny-2, ny-1 -> north's ghost rows -2, -1 (index 0, 1); my rows 0, 1 -> south's rows ny, ny+1
+                hl.north_ghost[k] = north + arr + k * comp
+                hl.south_ghost[k] = south + arr + k * comp + (H + ps["nyl_south"]) * nx * es
+        if wait:
+            hl.wait_north = me + flag_off + 4
+            hl.wait_south = me + flag_off
+        hl.signal_north = north + flag_off       # its flag[0]: "from south"
+        hl.signal_south = south + flag_off + 4   # its flag[1]: "from north"
+        return hl
 
     def _exchange_ghosts(self, st, idxs):
         """Fill the H ghost rows on both sides of the arrays `idxs` (owned rows sit at [H, H+nyl))."""
@@ -528,11 +578,24 @@ class FusedBandedFilter(BandedFilter):
         es = A[0].element_size()
 
         ncomp = st["ncomp"]
+        cache = st.setdefault("_ctypes", {})  # ctypes views built once per staging: the launches are host-bound on short bands
 
         def inner(k):  # the owned rows start H rows into the ghosted array
-            return [(A[k][c].data_ptr() + H * nx * es, nx, rows * nx) for c in range(ncomp)]
+            if ("in", k) not in cache:
+                cache[("in", k)] = lib.fields([(A[k][c].data_ptr() + H * nx * es, nx, rows * nx) for c in range(ncomp)])
+            return cache[("in", k)]
 
-        plain = [(bar[c].data_ptr(), nx, nyl * nx) for c in range(ncomp)]
+        if "bar" not in cache:
+            cache["bar"] = lib.fields([(bar[c].data_ptr(), nx, nyl * nx) for c in range(ncomp)])
+        plain = cache["bar"]
+
+        def halo(which, wait_value, signal_value, wait, push):
+            key = ("halo", which, wait, push)
+            if key not in cache:
+                cache[key] = self._push_halo(st, which, 0, 0, wait=wait, push=push)
+            hl = cache[key]
+            hl.wait_value, hl.signal_value = wait_value & 0xFFFFFFFF, signal_value & 0xFFFFFFFF
+            return hl
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
         x = 0
         A[0][:, :, H:H + nyl].copy_(st["X0"])
@@ -543,6 +606,30 @@ class FusedBandedFilter(BandedFilter):
         pairs = [(2, 3), (4, 5)]
         t1 = t2 = x
         cur, i = 0, 1
+        if st["push"] is not None:
+            # exchange fused into the kernels.  Flags only grow: block m of this call signals base + m and waits for
+            # base + m - 1; the first block waits for nothing (the exchange of the input above is a barrier across
+            # the ranks: everybody has finished the previous call).
+            nblk = (n + 1) // 2
+            base = self._epoch * (nblk + 1)
+            self._epoch += 1
+            m = 1
+            while i <= n:
+                kk = min(H, n - i + 1)
+                o1, o2 = pairs[cur]
+                if kk == 2:
+                    last = i + 1 == n
+                    h1 = halo(o1, base + m - 1, base + m, m > 1, not last)
+                    h2 = halo(o2, base + m - 1, base + m, m > 1, not last)
+                    lib.cheb_fused_halo(h, nb, i, 2, inner(t1), inner(t2), inner(o1), inner(o2), plain, h1, h2, stream)
+                else:  # odd step count: the one-step LAST kernel, waiting for the ghost rows the previous block pushed
+                    hl = halo(o1, base + m - 1, base + m, m > 1, False)
+                    lib.cheb_step_halo(h, nb, i, inner(t1), inner(t2), inner(o1), plain, hl, stream)
+                t1, t2 = o1, o2
+                cur ^= 1
+                i += kk
+                m += 1
+            return bar
         while i <= n:
             kk = min(H, n - i + 1)
             o1, o2 = pairs[cur]

@@ -192,6 +192,16 @@ typedef struct gcmf_halo {
  * but still signals (so that the neighbours know this rank has finished reading). */
 int gcmf_cheb_step_halo(gcmf_plan *plan, int64_t nb, int32_t step, const gcmf_field *t1_in, const gcmf_field *t2,
                         const gcmf_field *t0_out, const gcmf_field *bar, const gcmf_halo *halo, void *stream);
+/* gcmf_cheb_fused (vector operators, k = 2) on a band plan with the exchange fused in: the launch waits for the two
+ * ghost rows per side of `t1_in` / `t2_in` (flags of `halo_t1`), runs steps step and step+1, stores its first / last
+ * two rows of T_{step+1} into the neighbours' ghost rows described by `halo_t1` and those of T_step into the ones
+ * described by `halo_t2` (north_ghost[k]: the neighbour's ghost row mirroring my row ny-2, south_ghost[k]: the one
+ * mirroring my row 0; consecutive ghost rows are `t1_out[k].pitch` elements apart), and raises the neighbours' flags.
+ * The two halos share their flags, counters and batch strides.  A block that reaches n_steps pushes nothing but
+ * still signals.  One launch per two Chebyshev steps and rank, no NCCL call, no host synchronisation. */
+int gcmf_cheb_fused_halo(gcmf_plan *plan, int64_t nb, int32_t step, int32_t k, const gcmf_field *t1_in,
+                         const gcmf_field *t2_in, const gcmf_field *t1_out, const gcmf_field *t2_out,
+                         const gcmf_field *bar, const gcmf_halo *halo_t1, const gcmf_halo *halo_t2, void *stream);
 /* Push the border rows of `field` (the prepared input, before step 1) into the neighbours' ghost rows. */
 int gcmf_halo_push(gcmf_plan *plan, int64_t nb, const gcmf_field *field, const gcmf_halo *halo, void *stream);
 

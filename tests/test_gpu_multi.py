@@ -60,7 +60,7 @@ def _worker(rank, world, port, g, shape, q):
                                                    for o, s in zip(pouts, single))
         pbf.close()
         # temporal blocking on bands: 4 (scalar) / 2 (vector) ghost rows, one exchange per block of that many steps
-        for exch in ("nccl", "peer"):
+        for exch in (("nccl", "peer", "push") if len(fields) == 2 else ("nccl", "peer")):
             fbf = FusedBandedFilter(flt, rank, world, exchange=exch)
             for _ in range(2):
                 fouts, (fj0, fj1) = fbf.apply(*fields)

@@ -564,10 +564,14 @@ def test_fused_banded_single_rank_is_its_own_neighbour(g, shape):
             single = run_filter(flt, fields)
         finally:
             engine.set_steps_per_block(0)
-        fbf = FusedBandedFilter(flt, 0, 1)
-        for _ in range(2):
-            outs, (j0, j1) = fbf.apply(*fields)
-        fbf.close()
-        assert (j0, j1) == (0, shape[0])
-        for o, s in zip(outs, single):
-            assert np.array_equal(o, s, equal_nan=True), (g, scale, flt.n_steps)
+        for exch in (("nccl", "push") if len(fields) == 2 else ("nccl",)):
+            # "push": the exchange fused into the two-step kernel (peer stores + flags); with one rank the band pushes
+            # into its own ghost rows -- the same kernels and protocol as on several GPUs
+            fbf = FusedBandedFilter(flt, 0, 1, exchange=exch)
+            st = fbf.stage(*fields)
+            for _ in range(3):  # several runs on one staging: the flags keep growing
+                bar = fbf.run(st)
+            outs = tuple(bar[k].cpu().numpy() for k in range(len(fields)))
+            fbf.close()
+            for o, s in zip(outs, single):
+                assert np.array_equal(o, s, equal_nan=True), (g, scale, flt.n_steps, exch)
