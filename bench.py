@@ -557,7 +557,11 @@ def measure(ctx, args, name, nb=0, primary=False):
         fk = (f"cgrid2_kernel ({dom[1]} Chebyshev steps per launch, rows of all arrays streamed through TMA rings)"
               if cfg["grid_type"] == "VECTOR_C_GRID" else
               f"vec2_kernel ({dom[1]} Chebyshev steps per launch, rows streamed through TMA rings)"
-              if ncomp == 2 else f"fused_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)")
+              if ncomp == 2 else
+              f"march_kernel ({dom[1]} Chebyshev steps per launch, rows streamed through TMA rings, row windows in registers)"
+              if (cfg["grid_type"] in ("IRREGULAR_WITH_LAND", "MOM5U", "MOM5T") and w == 8
+                  and os.environ.get("GCMF_FUSED_FORM") != "tile") else
+              f"fused_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)")
         kname = {"fused": fk, "fused_first": fk + ", first block", "fused_last": fk + ", last block",
                  "mid": "step_kernel<MODE_MID> (one Chebyshev step)", "first": "step_kernel<MODE_FIRST>",
                  "last": "step_kernel<MODE_LAST>"}[dom[0]]

@@ -11,8 +11,12 @@
 //     one level) performs step 1 at row t, step 2 at row t-2, ... step K at row t-2(K-1).  Every input of every step
 //     was produced in an earlier iteration, so the K steps of an iteration are INDEPENDENT (a first version with the
 //     steps one row apart fed each step's result to the next one as its north neighbour: four dependent fp64 chains per
-//     iteration, 1.3x slower than the tile form).  The N / S neighbours of a point are registers of the same thread
-//     (three rows per stage), there is NO redundant row work inside a band (the tile form recomputes 4 halo rows per 24);
+//     iteration, 1.3x slower than the tile form).  The N / S neighbours of a point are registers of the same thread,
+//     there is NO redundant row work inside a band (the tile form recomputes 4 halo rows per 24);
+//   * the row windows of the pipeline (three to five rows of every stage) live in ROW-KEYED register slots and the
+//     iterations are unrolled by eight (MarchConsumer): advancing a window is register renaming, not data movement.
+//     (The first form of this kernel shifted the windows with 67 register moves per iteration -- 23 % of its
+//     instructions -- and ran level with the tile form, 101.6 vs 100.9 ms per cfg3 filter call; this one takes 84.7 ms.)
 //   * only the W / E neighbours go through shared memory: at the top of an iteration every thread publishes the K
 //     values that become stage centres in the next iteration (sanitized) in a double-buffered exchange row -- one named
 //     barrier per iteration and level (128 threads);
@@ -24,11 +28,11 @@
 //     warp 0 instead made the whole CTA run at that warp's pace -- measured 1.3x to 2x slower than the tile form.)
 //
 // HBM traffic per grid-point step: (6w + 3w/LV) / K * (128/120) = 14.4 B (fp64, K = 4) plus 3(K-1) priming iterations
-// per band, against 13.1 B of the tile form -- but all 16 warps do the same work, the per-step shared-memory traffic is
-// 7 LDS.64 + 1 STS.64 per point instead of a full tile sweep.
+// per band; measured 12.8 B (ncu, 400-row bands; the halo columns hit in L2).  All 12 consumer warps do the same work;
+// the per-step shared-memory traffic is 7 LDS.64 + 1 STS.64 per point instead of a full tile sweep.
 //
 // The arithmetic of a point is the same inline code as everywhere else (flux_lap, shifted_flux, cheb_next,
-// bar_update): results are bit-identical to the tile form and to the one-step kernels.
+// bar_update): results are bit-identical to the tile form and to the one-step kernels (GPU tests).
 // Device-only: the host emulator keeps the tile form (tests/cabi/gpu_vs_emu.c compares the GPU with it bit for bit).
 #pragma once
 #include "gcmf_fused.cuh"
@@ -62,6 +66,167 @@ template <typename T> struct MarchGeom {
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// The consumer side of march_kernel: one thread = one column of one level.
+//
+// Pipeline state, keyed by ROW.  Stage q (0..K-1) is the input field of step q+1, which runs at row t-2q in iteration t.
+// A value that belongs to row r of stage q lives in register slot (r - t0) & 7 of that stage's window:
+//   raw[q][.]  raw stage-q values        (rows t-2q-2 .. t-2q+1 are live: the "-x" term of step q+1 and T_{i-2} of step q+2)
+//   san[q][.]  nan_to_num'ed values      (rows t-2q-1 .. t-2q+1: south, centre, north of step q+1)
+//   acc[q][.]  running bar after step q+1 (rows t-2q-2, t-2q-1: consumed by step q+2 two iterations later)
+// With iterations unrolled by eight (iteration<PH>: PH = (t - t0) & 7) every slot index is a compile-time constant, so
+// advancing the windows one row north costs no instruction (the first form of this kernel spent 67 of its 287
+// instructions per iteration on those register moves); the exchange-row parity and the state-ring slots are
+// compile-time too.
+template <typename T, int EDGE, int K> struct MarchConsumer {
+    using G = MarchGeom<T>;
+    static constexpr bool FIRST = (EDGE & 1) != 0, LAST = (EDGE & 2) != 0;
+    static constexpr int W = 8;
+    static constexpr int XBP = MARCH_LV * FUSED_H * MARCH_W;
+    static constexpr int oCe = 0, oCn = MARCH_W, oRa = 2 * MARCH_W;  // arrays inside a coefficient slot
+    T raw[K][W], san[K][W], acc[K][W];
+    const FusedParams<T>* P;
+    T* xb0;               // this thread's entry of the exchange rows, parity 0 (parity 1: + XBP)
+    const T* cring_c;     // this thread's column of the coefficient ring
+    const T* sring_c;     // ... of the state ring
+    uint64_t *fullS, *emptyS, *fullC, *emptyC;
+    int l, lane0, j0, j1, R0, last_idx, oT1, oT2, oBar;
+    bool emit_col;
+    T cc;
+    int64_t ob, o1, o2;   // running element offsets of the output row
+
+    __device__ __forceinline__ void init(const FusedParams<T>& P_, T* xb, T* cring, T* sring, uint64_t* fS, uint64_t* eS,
+                                         uint64_t* fC, uint64_t* eC, int l_, int c, int64_t lev, int cx, int j0_, int j1_,
+                                         int nrows, int R0_) {
+        P = &P_;
+        l = l_;
+        lane0 = (threadIdx.x & 31) == 0;
+        j0 = j0_; j1 = j1_; R0 = R0_;
+        last_idx = nrows - 1;
+        fullS = fS; emptyS = eS; fullC = fC; emptyC = eC;
+        xb0 = xb + (size_t)l * FUSED_H * MARCH_W + c;
+        cring_c = cring + c;
+        sring_c = sring + c;
+        oT1 = 3 * l * MARCH_W; oT2 = oT1 + MARCH_W; oBar = oT2 + MARCH_W;
+        const int gc = cx * G::SW + c - G::H;  // global column (unwrapped)
+        emit_col = c >= G::H && c < MARCH_W - G::H && gc < P_.g.nx;
+        cc = (T)P_.c;
+        const int t0 = j0 - (K - 1);
+        ob = lev * P_.bar.bstride + (int64_t)(t0 - 2 * (K - 1)) * P_.bar.pitch + gc;
+        o1 = o2 = 0;
+        if (!LAST) {
+            o1 = lev * P_.t1_out.bstride + (int64_t)(t0 - 2 * (K - 1)) * P_.t1_out.pitch + gc;
+            o2 = lev * P_.t2_out.bstride + (int64_t)(t0 - 2 * (K - 1)) * P_.t2_out.pitch + gc;
+        }
+#pragma unroll
+        for (int q = 0; q < K; ++q)
+#pragma unroll
+            for (int w = 0; w < W; ++w) raw[q][w] = san[q][w] = acc[q][w] = T(0);
+    }
+    __device__ __forceinline__ const T* srow(int slot) const { return sring_c + (size_t)slot * G::SSLOT; }
+    __device__ __forceinline__ const T* crow(int idx) const { return cring_c + (size_t)(idx & (MARCH_DC - 1)) * G::CSLOT; }
+
+    // stage 0 holds rows t0-1, t0, t0+1 (staged indices 0, 1, 2 = slots 7, 0, 1); coefficient rows 0 and 1
+    __device__ __forceinline__ void prologue() {
+        mbar_wait(&fullS[0], 0);
+        mbar_wait(&fullS[1], 0);
+        mbar_wait(&fullS[2], 0);
+        mbar_wait(&fullC[0], 0);
+        raw[0][7] = srow(0)[oT1];
+        raw[0][0] = srow(1)[oT1];
+        raw[0][1] = srow(2)[oT1];
+        san[0][7] = nan2num(raw[0][7]);
+        san[0][0] = nan2num(raw[0][0]);
+        san[0][1] = nan2num(raw[0][1]);
+        xb0[0] = san[0][0];  // what the neighbours read as stage-0 centre in the first iteration
+#pragma unroll
+        for (int q = 1; q < FUSED_H; ++q) xb0[q * MARCH_W] = T(0);
+        // state row 0 (row t0-1) only contributes its T1, lifted just now: release its slot (iteration t releases row t,
+        // starting with staged index 1)
+        __syncwarp();
+        if (lane0) mbar_arrive(&emptyS[0]);
+        named_barrier(1 + l, MARCH_W);
+    }
+
+    // iteration t = t0 + 8 g + PH
+    template <int PH> __device__ __forceinline__ void iteration(int t, int g) {
+        constexpr int TI0 = 1 + PH;                // staged index of row t is TI0 + 8 g (row t0 is staged index 1)
+        const int ti = TI0 + 8 * g;
+        T* const xr = xb0 + (PH & 1) * XBP;        // exchange rows read in this iteration ...
+        T* const xw = xb0 + ((PH + 1) & 1) * XBP;  // ... and written for the next one
+        // publish what becomes the stage centres of the next iteration: the north rows held now
+#pragma unroll
+        for (int q = 0; q < K; ++q) xw[q * MARCH_W] = san[q][(PH - 2 * q + 1) & 7];
+        // new north row of stage 0 for the next iteration: input row t+2
+        T rawN0 = T(0);
+        if (ti + 2 <= last_idx) {
+            mbar_wait(&fullS[(TI0 + 2) & 7], (unsigned)((g + ((TI0 + 2) >> 3)) & 1));
+            rawN0 = srow((TI0 + 2) & 7)[oT1];
+        }
+        if (ti <= last_idx) mbar_wait(&fullC[ti & (MARCH_DC - 1)], (unsigned)((ti / MARCH_DC) & 1));
+        T t2in = T(0), barin = T(0);
+        if (!FIRST && ti <= last_idx) {
+            t2in = srow(TI0 & 7)[oT2];
+            if (t >= j0 && t < j1) barin = srow(TI0 & 7)[oBar];
+        }
+        T tn[K], an[K];
+#pragma unroll
+        for (int s = 1; s <= K; ++s) {
+            const int q = s - 1;
+            const int r = t - 2 * q;
+            // step s at row r feeds an owned row only inside the dependency cone of the band (uniform over the CTA)
+            const bool active = r >= j0 - (K - s) && r <= j1 - 1 + (K - s);
+            tn[q] = T(0);
+            an[q] = T(0);
+            if (active) {
+                const T* cr = crow(ti - 2 * q);       // coefficient row r
+                const T* crs = crow(ti - 2 * q - 1);  // row r-1: its north faces are the south faces of row r
+                const T lap = flux_lap<T>(san[q][(PH - 2 * q) & 7], xr[q * MARCH_W - 1], xr[q * MARCH_W + 1],
+                                          san[q][(PH - 2 * q + 1) & 7], san[q][(PH - 2 * q - 1) & 7], cr[oCe], cr[oCe - 1],
+                                          cr[oCn], crs[oCn], cr[oRa]);
+                const T a = shifted_flux<T>(raw[q][(PH - 2 * q) & 7], cc, lap);             // filter.py:171
+                const bool start = FIRST && s == 1;
+                // T_{i-2} of this step: the previous stage's value at the same row r
+                const T tm2 = s == 1 ? t2in : raw[q >= 1 ? q - 1 : 0][(PH - 2 * q) & 7];
+                tn[q] = start ? a : cheb_next<T>(a, tm2);                                    // filter.py:192-194 / 197-203
+                const double b0 = s == 1 ? (start ? P->p0 * (double)raw[0][PH & 7] : (double)barin)
+                                         : (double)acc[q >= 1 ? q - 1 : 0][(PH - 2 * q) & 7];
+                an[q] = (T)bar_update(b0, P->p[q], (double)tn[q]);                          // filter.py:195 / 204
+            }
+        }
+        // outputs of row rk = t-2(K-1): T_{i+K-1} = the value step K produced, T_{i+K-2} = the centre of stage K-1
+        const int rk = t - 2 * (K - 1);
+        if (emit_col && rk >= j0 && rk < j1) {
+            if (!LAST) {
+                P->t1_out.p[o1] = tn[K - 1];
+                P->t2_out.p[o2] = raw[K - 1][(PH - 2 * (K - 1)) & 7];
+            }
+            P->bar.p[ob] = an[K - 1];
+        }
+        ob += P->bar.pitch;
+        if (!LAST) {
+            o1 += P->t1_out.pitch;
+            o2 += P->t2_out.pitch;
+        }
+        // the value step q produced at row t-2(q-1) is the new north row (row t-2q+2) of stage q; nothing moves
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            const T nraw = q == 0 ? rawN0 : tn[q >= 1 ? q - 1 : 0];
+            raw[q][(PH - 2 * q + 2) & 7] = nraw;
+            san[q][(PH - 2 * q + 2) & 7] = nan2num(nraw);
+            acc[q][(PH - 2 * q) & 7] = an[q];
+        }
+        // releases: state row t is done (T2 / bar read above; its T1 was lifted two iterations ago); coefficient row
+        // t-2K+1 was last used as the south faces of step K's row
+        __syncwarp();
+        if (lane0) {
+            if (ti <= last_idx) mbar_arrive(&emptyS[TI0 & 7]);
+            const int ci = ti - 2 * K + 1;
+            if (ci >= 0 && ci <= last_idx) mbar_arrive(&emptyC[ci & (MARCH_DC - 1)]);
+        }
+        named_barrier(1 + l, MARCH_W);
+    }
+};
 
 // EDGE as in fused_kernel: bit 0 = the block starts at recurrence step 1, bit 1 = it ends at step n_steps.
 // K = steps of the block (compile time: the step loop is straight-line code).
@@ -161,135 +326,23 @@ __global__ void __launch_bounds__(MarchGeom<T>::NTHREADS, 1)
     // ---- consumers: thread = (level l, column c)
     const int l = tid / MARCH_W, c = tid % MARCH_W;
     if (l >= nlev) return;
-    const int64_t lev = lev0 + l;
-    const int gc = cx * G::SW + c - H;  // global column (unwrapped)
-    const bool emit_col = c >= H && c < MARCH_W - H && gc < nx;
-    const T cc = (T)P.c;
-    const int oT1 = 3 * l * MARCH_W, oT2 = oT1 + MARCH_W, oBar = oT2 + MARCH_W;  // arrays inside a state slot
-    constexpr int oCe = 0, oCn = MARCH_W, oRa = 2 * MARCH_W;                      // arrays inside a coefficient slot
-    const T* const sring_c = sring + c;
-    const T* const cring_c = cring + c;
-    // ring row of staged index idx (= row - R0)
-    auto srow = [&](int idx) { return sring_c + (size_t)(idx & (MARCH_DS - 1)) * G::SSLOT; };
-    auto crow = [&](int idx) { return cring_c + (size_t)(idx & (MARCH_DC - 1)) * G::CSLOT; };
-    constexpr int XBP = MARCH_LV * FUSED_H * MARCH_W;
-    T* xr = xb + (size_t)l * FUSED_H * MARCH_W + c;  // exchange rows read in this iteration ...
-    T* xw = xr + XBP;                                // ... and written for the next one
-    auto wait_full = [&](uint64_t* fullb, int D, int idx) { mbar_wait(&fullb[idx & (D - 1)], (unsigned)((idx / D) & 1)); };
-
-    // ---- per-thread pipeline state.  Stage q (0..K-1) is the input of step q+1, which runs at row t-2q in iteration t:
-    //   san{S,C,N}[q]  sanitized stage-q values at rows t-2q-1, t-2q, t-2q+1
-    //   raw{SS,S,C,N}[q]  raw values at rows t-2q-2 .. t-2q+1 (C: the "-x" term of step q+1; SS: T_{i-2} of step q+2)
-    //   accA / accB[q]  running bar of the rows that finished step q+1 one / two iterations ago
-    T sanS[K], sanC[K], sanN[K], rawSS[K], rawS[K], rawC[K], rawN[K], accA[K], accB[K];
-#pragma unroll
-    for (int q = 0; q < K; ++q)
-        sanS[q] = sanC[q] = sanN[q] = rawSS[q] = rawS[q] = rawC[q] = rawN[q] = accA[q] = accB[q] = T(0);
+    MarchConsumer<T, EDGE, K> cs;
+    cs.init(P, xb, cring, sring, fullS, emptyS, fullC, emptyC, l, c, lev0 + l, cx, j0, j1, nrows, R0);
+    cs.prologue();
+    // Eight iterations per trip: every register slot, exchange-row parity and state-ring slot below is a compile-time
+    // function of the phase, so the row windows of the pipeline rotate by renaming instead of by register moves.
     const int t0 = j0 - (K - 1), t1 = j1 - 1 + 2 * (K - 1);
-    const int last_idx = nrows - 1;
-    {   // prologue: stage 0 holds rows t0-1, t0, t0+1 (staged indices 0, 1, 2); coefficient rows 0 and 1
-        wait_full(fullS, MARCH_DS, 0);
-        wait_full(fullS, MARCH_DS, 1);
-        wait_full(fullS, MARCH_DS, 2);
-        wait_full(fullC, MARCH_DC, 0);
-        rawS[0] = srow(0)[oT1];
-        rawC[0] = srow(1)[oT1];
-        rawN[0] = srow(2)[oT1];
-        sanS[0] = nan2num(rawS[0]);
-        sanC[0] = nan2num(rawC[0]);
-        sanN[0] = nan2num(rawN[0]);
-        xr[0] = sanC[0];  // what the neighbours read as stage-0 centre in the first iteration
-#pragma unroll
-        for (int q = 1; q < FUSED_H; ++q) xr[q * MARCH_W] = T(0);
-        // state row 0 (row t0-1) only contributes its T1, lifted just now: release its slot (the loop releases row t in
-        // iteration t, starting with staged index 1)
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&emptyS[0]);
-        named_barrier(1 + l, MARCH_W);
-    }
-    // running element offsets of the output rows (row rk = t - 2(K-1))
-    int64_t ob = lev * P.bar.bstride + (int64_t)(t0 - 2 * (K - 1)) * P.bar.pitch + gc;
-    int64_t o1 = 0, o2 = 0;
-    if (!LAST) {
-        o1 = lev * P.t1_out.bstride + (int64_t)(t0 - 2 * (K - 1)) * P.t1_out.pitch + gc;
-        o2 = lev * P.t2_out.bstride + (int64_t)(t0 - 2 * (K - 1)) * P.t2_out.pitch + gc;
-    }
-#pragma unroll 1
-    for (int t = t0; t <= t1; ++t) {
-        const int ti = t - R0;  // staged index of row t
-        // publish what becomes the stage centres of the next iteration: the north rows held now
-#pragma unroll
-        for (int q = 0; q < K; ++q) xw[q * MARCH_W] = sanN[q];
-        // new north row of stage 0 for the next iteration: input row t+2
-        T rawN0 = T(0);
-        if (ti + 2 <= last_idx) {
-            wait_full(fullS, MARCH_DS, ti + 2);
-            rawN0 = srow(ti + 2)[oT1];
-        }
-        if (ti <= last_idx) wait_full(fullC, MARCH_DC, ti);
-        T t2in = T(0), barin = T(0);
-        if (!FIRST && ti <= last_idx) {
-            t2in = srow(ti)[oT2];
-            if (t >= j0 && t < j1) barin = srow(ti)[oBar];
-        }
-        T tn[K], an[K];
-#pragma unroll
-        for (int s = 1; s <= K; ++s) {
-            const int q = s - 1;
-            const int r = t - 2 * q;
-            // step s at row r feeds an owned row only inside the dependency cone of the band (uniform over the CTA)
-            const bool active = r >= j0 - (K - s) && r <= j1 - 1 + (K - s);
-            tn[q] = T(0);
-            an[q] = T(0);
-            if (active) {
-                const T* cr = crow(ti - 2 * q);       // coefficient row r
-                const T* crs = crow(ti - 2 * q - 1);  // row r-1: its north faces are the south faces of row r
-                const T lap = flux_lap<T>(sanC[q], xr[q * MARCH_W - 1], xr[q * MARCH_W + 1], sanN[q], sanS[q],
-                                          cr[oCe], cr[oCe - 1], cr[oCn], crs[oCn], cr[oRa]);
-                const T a = shifted_flux<T>(rawC[q], cc, lap);                           // filter.py:171
-                const bool start = FIRST && s == 1;
-                const T tm2 = s == 1 ? t2in : rawSS[q >= 1 ? q - 1 : 0];
-                tn[q] = start ? a : cheb_next<T>(a, tm2);                                 // filter.py:192-194 / 197-203
-                const double b0 = s == 1 ? (start ? P.p0 * (double)rawC[0] : (double)barin) : (double)accB[q >= 1 ? q - 1 : 0];
-                an[q] = (T)bar_update(b0, P.p[q], (double)tn[q]);                        // filter.py:195 / 204
-            }
-        }
-        // outputs of row rk = t-2(K-1): T_{i+K-1} = the value step K produced, T_{i+K-2} = the centre of stage K-1
-        const int rk = t - 2 * (K - 1);
-        if (emit_col && rk >= j0 && rk < j1) {
-            if (!LAST) {
-                P.t1_out.p[o1] = tn[K - 1];
-                P.t2_out.p[o2] = rawC[K - 1];
-            }
-            P.bar.p[ob] = an[K - 1];
-        }
-        ob += P.bar.pitch;
-        if (!LAST) {
-            o1 += P.t1_out.pitch;
-            o2 += P.t2_out.pitch;
-        }
-        // shift every window one row north; the value step q produced enters stage q as its new north row
-#pragma unroll
-        for (int q = 0; q < K; ++q) {
-            const T nraw = q == 0 ? rawN0 : tn[q >= 1 ? q - 1 : 0];
-            rawSS[q] = rawS[q]; rawS[q] = rawC[q]; rawC[q] = rawN[q]; rawN[q] = nraw;
-            sanS[q] = sanC[q]; sanC[q] = sanN[q]; sanN[q] = nan2num(nraw);
-            accB[q] = accA[q]; accA[q] = an[q];
-        }
-        // releases: state row t is done (T2 / bar read above; its T1 was lifted two iterations ago); coefficient row
-        // t-2K+1 was last used as the south faces of step K's row
-        __syncwarp();
-        if ((tid & 31) == 0) {
-            if (ti >= 0 && ti <= last_idx) mbar_arrive(&emptyS[ti & (MARCH_DS - 1)]);
-            const int ci = ti - 2 * K + 1;
-            if (ci >= 0 && ci <= last_idx) mbar_arrive(&emptyC[ci & (MARCH_DC - 1)]);
-        }
-        {   // swap the exchange rows
-            T* tmp = xr;
-            xr = xw;
-            xw = tmp;
-        }
-        named_barrier(1 + l, MARCH_W);
+    for (int t = t0, g = 0; t <= t1; t += 8, ++g) {
+        // (iterations beyond t1 in the last trip are no-ops: every wait, step, store and release below is guarded by
+        // its row range, so the trip needs no per-iteration branch)
+        cs.template iteration<0>(t, g);
+        cs.template iteration<1>(t + 1, g);
+        cs.template iteration<2>(t + 2, g);
+        cs.template iteration<3>(t + 3, g);
+        cs.template iteration<4>(t + 4, g);
+        cs.template iteration<5>(t + 5, g);
+        cs.template iteration<6>(t + 6, g);
+        cs.template iteration<7>(t + 7, g);
     }
 }
 #endif

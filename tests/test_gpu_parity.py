@@ -332,27 +332,36 @@ def test_pipelined_host_path_matches_monolithic():
     assert rel_l2(piped, ref) < TOL64
 
 
-def test_fused_neighbour_sync_is_deterministic():
-    """The flux kernel replaces the CTA barrier by per-warp mbarriers between neighbouring warps
-    (compute-sanitizer racecheck only models CTA barriers).  A missing dependency would show
-    up as run-to-run differences: 25 repetitions must agree bit for bit with each other and with the
-    barrier-free one-step kernels."""
+@pytest.mark.parametrize("g", ["IRREGULAR_WITH_LAND", "TRIPOLAR_POP_WITH_LAND"])
+def test_fused_neighbour_sync_is_deterministic(g):
+    """Both fused FLUX kernels order their shared-memory traffic with mbarriers instead of CTA barriers (the tile form:
+    per-warp barriers between neighbouring warps -- it runs the tripolar grid here; the row-streaming form: TMA ring
+    full / empty barriers + one named barrier per level and row -- it runs the periodic grid), which compute-sanitizer
+    racecheck does not model.  A missing dependency would show up as run-to-run differences: 25 repetitions must agree
+    bit for bit with each other and with the barrier-free one-step kernels (to rounding across the tripolar fold)."""
     import torch
     from gcm_filters_b200 import engine
-    (f,), gv = fixtures.fixture("IRREGULAR_WITH_LAND", (480, 720))
+    (f,), gv = fixtures.fixture(g, (480, 720))
     rng = np.random.default_rng(9)
     fb = f[None] * (1 + 0.2 * rng.standard_normal((6, 1, 1)))
     fb[:, gv["wet_mask"] == 0] = np.nan
-    flt = make_filter("IRREGULAR_WITH_LAND", gv, filter_scale=16.0, dx_min=1.0)
+    flt = make_filter(g, gv, filter_scale=16.0, dx_min=1.0)
     t = torch.as_tensor(fb).cuda()
     try:
         engine.set_steps_per_block(1)
         plain = flt.apply(t, None).clone()
     finally:
         engine.set_steps_per_block(0)
+    first = None
     for rep in range(25):
         out = flt.apply(t, None)
-        assert torch.equal(torch.nan_to_num(out, nan=-1.0), torch.nan_to_num(plain, nan=-1.0)), rep
+        if g == "IRREGULAR_WITH_LAND":
+            assert torch.equal(torch.nan_to_num(out, nan=-1.0), torch.nan_to_num(plain, nan=-1.0)), rep
+        elif first is None:
+            first = out.clone()
+            assert rel_l2(first.cpu().numpy(), plain.cpu().numpy()) < 1e-14
+        else:
+            assert torch.equal(torch.nan_to_num(out, nan=-1.0), torch.nan_to_num(first, nan=-1.0)), rep
 
 
 def test_full_size_pop_slice_vs_oracle_and_properties():
@@ -575,3 +584,35 @@ def test_fused_banded_single_rank_is_its_own_neighbour(g, shape):
             fbf.close()
             for o, s in zip(outs, single):
                 assert np.array_equal(o, s, equal_nan=True), (g, scale, flt.n_steps, exch)
+
+
+def test_fused_flux_march_form_is_bit_identical_to_tile_form():
+    """The row-streaming form of the fused FLUX steps (march_kernel, opt-in with GCMF_FUSED_FORM=march): same per-point
+    arithmetic as the tile form and the one-step kernels -> identical bits.  Whole grids with several strips and row
+    bands, level groups that do not divide the batch, step counts that end with a short block, NaN on land."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    code = (
+        "import numpy as np, sys\n"
+        "from gcm_filters_b200 import Filter, GridType\n"
+        "from oracle import fixtures\n"
+        "out = {}\n"
+        "for shape, nb, scale in (((96, 264), 4, 8.0), ((150, 520), 7, 6.0), ((64, 136), 1, 9.0)):\n"
+        "    (f,), gv = fixtures.fixture('IRREGULAR_WITH_LAND', shape)\n"
+        "    rng = np.random.default_rng(3)\n"
+        "    fb = f[None] * (1 + 0.2 * rng.standard_normal((nb, 1, 1)))\n"
+        "    fb[:, gv['wet_mask'] == 0] = np.nan\n"
+        "    flt = Filter(filter_scale=scale, dx_min=1.0, grid_type=GridType.IRREGULAR_WITH_LAND, grid_vars=gv)\n"
+        "    out[str(shape)] = flt.apply(fb, None)\n"
+        "np.savez(sys.argv[1], **out)\n")
+    with tempfile.TemporaryDirectory() as tmp:
+        res = {}
+        for form in ("tile", "march"):
+            path = os.path.join(tmp, form + ".npz")
+            env = dict(os.environ, GCMF_FUSED_FORM=form, PYTHONPATH=os.pathsep.join(sys.path))
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+            res[form] = dict(np.load(path))
+        for key in res["tile"]:
+            assert np.array_equal(res["tile"][key], res["march"][key], equal_nan=True), key
