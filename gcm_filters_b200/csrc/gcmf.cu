@@ -1251,18 +1251,20 @@ static int launch_fused_kernel(gcmf_plan* pl, const FusedParams<T>& P, int64_t n
 // ---- row-streaming form of the fused FLUX steps (gcmf_march.cuh) ----------------------------------------------
 // The DEFAULT for fp64 FLUX plans on whole doubly periodic grids (cfg3) since its consumer keeps the row windows in
 // row-keyed register slots (gcmf_march.cuh): measured on a B200 against the tile form (profiles/variants_r02c_march.log,
-// ncu_r02c_march8_cfg3.*): cfg3 nb = 62: 84.7 vs 100.9 ms per filter call (278 vs 234 G units/s), nb = 8: 13.0 vs 13.9 ms;
-// 4.1 G warp instructions per 4-step launch against 6.1 G.  The tile form keeps the tripolar grids (the fold), the
+// ncu_r02c_march8_cfg3.*): cfg3 nb = 62: 80.5 vs 100.9 ms per filter call (293 vs 234 G units/s), nb = 8: 12.3 vs 13.9 ms;
+// 4.1 G warp instructions per 4-step launch against 6.1 G (before the check-free steady-state iterations: fewer still).  The tile form keeps the tripolar grids (the fold), the
 // latitude bands, grids narrower than one strip and fp32 (63.8 vs 77.8 ms on the cfg3 shape: twice the columns per tile
 // row).  GCMF_FUSED_FORM=tile|march forces one form where both are eligible (A/B, tests).
-template <typename T> static bool march_eligible(const gcmf_plan* pl) {
+template <typename T> static bool march_eligible(const gcmf_plan* pl, int64_t nb) {
     static const char* force = getenv("GCMF_FUSED_FORM");
     if (force && !strcmp(force, "tile")) return false;
     if (pl->desc.op != GCMF_OP_FLUX) return false;
     if (pl->desc.flags & (GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S)) return false;
     if (pl->desc.nx < MARCH_W) return false;
     if (force && !strcmp(force, "march")) return true;  // incl. latitude bands and fp32
-    return sizeof(T) == 8 && (pl->desc.flags & GCMF_FLAG_WRAP_Y) != 0;
+    // a CTA marches MARCH_LV = 3 levels at once (3.8 ms per group of three on the cfg3 grid, against 1.6 - 2.3 ms per level
+    // of the tile form): batches of 1, 2 or 4 levels leave too many of its level slots empty
+    return sizeof(T) == 8 && (pl->desc.flags & GCMF_FLAG_WRAP_Y) != 0 && nb >= 3 && nb != 4;
 }
 
 template <typename T, int EDGE, int K> static int launch_march_t(const gcmf_plan* pl, const FusedParams<T>& P, cudaStream_t st) {
@@ -1277,10 +1279,11 @@ template <typename T, int EDGE, int K> static int launch_march_t(const gcmf_plan
     }
     const int nstrips = (P.g.nx + G::SW - 1) / G::SW;
     const int nlg = (int)((P.nb + MARCH_LV - 1) / MARCH_LV);
-    // Rows per band: 3(K-1) priming iterations per band against enough CTAs for a dozen rounds of the device (the tail
-    // of a launch is one CTA long).  Measured on cfg3, ms per filter call: nb = 62 (630 CTAs per band): 60 rows 95.5,
-    // 120: 89.1, 240: 85.4, 400: 84.7, 600: 84.9, 800: 85.3, 1200: 86.9, 2400: 98.8; nb = 8 (90 CTAs per band):
-    // 120 rows 13.0, 240: 13.4, 600: 15.2, 1200: 20.8.
+    // Rows per band: 3(K-1) priming iterations per band against enough CTAs for nine rounds of the device (the tail of
+    // a launch is one CTA long): the tallest band of at most 400 rows that leaves that many.  Measured on cfg3, ms per
+    // filter call: nb = 62 (630 CTAs per band): 200 rows 82.3, 400: 80.5, 800: 81.6 (before the steady-state
+    // iterations: 60: 95.5, 120: 89.1, 240: 85.4, 400: 84.7, 600: 84.9, 1200: 86.9, 2400: 98.8); nb = 8 (90 CTAs per
+    // band): 50 rows 13.5, 75: 12.7, 100: 12.3, 150: 12.1, 200: 12.5, 300: 12.5.
     int ry = 400;
     {
         const char* e = getenv("GCMF_MARCH_ROWS");
@@ -1289,7 +1292,7 @@ template <typename T, int EDGE, int K> static int launch_march_t(const gcmf_plan
             ry = v;
         } else {
             const int64_t per_band = (int64_t)nstrips * nlg;
-            while (ry > 24 && per_band * ((P.g.ny + ry - 1) / ry) < 12 * (int64_t)pl->sm_count) ry = (ry + 1) / 2;
+            while (ry > 24 && per_band * ((P.g.ny + ry - 1) / ry) < 9 * (int64_t)pl->sm_count) --ry;
         }
     }
     const int64_t nbands = (P.g.ny + ry - 1) / ry;
@@ -1533,7 +1536,7 @@ static int run_fused_t(gcmf_plan* pl, int64_t nb, int step0, int k, const gcmf_f
     gcmf_count_launch(1);
     return GCMF_OK;
 #else
-    if (kind == FK_FLUX && march_eligible<T>(pl)) return launch_march<T>(pl, P, st);
+    if (kind == FK_FLUX && march_eligible<T>(pl, nb)) return launch_march<T>(pl, P, st);
     if (kind == FK_FLUX) return launch_fused_kernel<T, FK_FLUX>(pl, P, ncta, st);
     return launch_fused_kernel<T, FK_REG5>(pl, P, ncta, st);
 #endif

@@ -16,7 +16,8 @@
 //   * the row windows of the pipeline (three to five rows of every stage) live in ROW-KEYED register slots and the
 //     iterations are unrolled by eight (MarchConsumer): advancing a window is register renaming, not data movement.
 //     (The first form of this kernel shifted the windows with 67 register moves per iteration -- 23 % of its
-//     instructions -- and ran level with the tile form, 101.6 vs 100.9 ms per cfg3 filter call; this one takes 84.7 ms.)
+//     instructions -- and ran level with the tile form, 101.6 vs 100.9 ms per cfg3 filter call; this one took 84.7 ms,
+//     and 80.5 ms once the trips inside a band run iterations compiled without the CTA-uniform range checks.)
 //   * only the W / E neighbours go through shared memory: at the top of an iteration every thread publishes the K
 //     values that become stage centres in the next iteration (sanitized) in a double-buffered exchange row -- one named
 //     barrier per iteration and level (128 threads);
@@ -148,8 +149,11 @@ template <typename T, int EDGE, int K> struct MarchConsumer {
         named_barrier(1 + l, MARCH_W);
     }
 
-    // iteration t = t0 + 8 g + PH
-    template <int PH> __device__ __forceinline__ void iteration(int t, int g) {
+    // iteration t = t0 + 8 g + PH.  STEADY: the caller guarantees j0 + 2(K-1) <= t <= j1 - 1 -- every staged row exists,
+    // every step is active, the output row is owned -- so none of the (CTA-uniform) range checks below is compiled in:
+    // 50 of the 224 instructions of a generic iteration are those checks, their branches and the zeroing / selects of the
+    // values they guard.
+    template <int PH, bool STEADY> __device__ __forceinline__ void iteration(int t, int g) {
         constexpr int TI0 = 1 + PH;                // staged index of row t is TI0 + 8 g (row t0 is staged index 1)
         const int ti = TI0 + 8 * g;
         T* const xr = xb0 + (PH & 1) * XBP;        // exchange rows read in this iteration ...
@@ -159,15 +163,15 @@ template <typename T, int EDGE, int K> struct MarchConsumer {
         for (int q = 0; q < K; ++q) xw[q * MARCH_W] = san[q][(PH - 2 * q + 1) & 7];
         // new north row of stage 0 for the next iteration: input row t+2
         T rawN0 = T(0);
-        if (ti + 2 <= last_idx) {
+        if (STEADY || ti + 2 <= last_idx) {
             mbar_wait(&fullS[(TI0 + 2) & 7], (unsigned)((g + ((TI0 + 2) >> 3)) & 1));
             rawN0 = srow((TI0 + 2) & 7)[oT1];
         }
-        if (ti <= last_idx) mbar_wait(&fullC[ti & (MARCH_DC - 1)], (unsigned)((ti / MARCH_DC) & 1));
+        if (STEADY || ti <= last_idx) mbar_wait(&fullC[ti & (MARCH_DC - 1)], (unsigned)((ti / MARCH_DC) & 1));
         T t2in = T(0), barin = T(0);
-        if (!FIRST && ti <= last_idx) {
+        if (!FIRST && (STEADY || ti <= last_idx)) {
             t2in = srow(TI0 & 7)[oT2];
-            if (t >= j0 && t < j1) barin = srow(TI0 & 7)[oBar];
+            if (STEADY || (t >= j0 && t < j1)) barin = srow(TI0 & 7)[oBar];
         }
         T tn[K], an[K];
 #pragma unroll
@@ -175,7 +179,7 @@ template <typename T, int EDGE, int K> struct MarchConsumer {
             const int q = s - 1;
             const int r = t - 2 * q;
             // step s at row r feeds an owned row only inside the dependency cone of the band (uniform over the CTA)
-            const bool active = r >= j0 - (K - s) && r <= j1 - 1 + (K - s);
+            const bool active = STEADY || (r >= j0 - (K - s) && r <= j1 - 1 + (K - s));
             tn[q] = T(0);
             an[q] = T(0);
             if (active) {
@@ -196,7 +200,7 @@ template <typename T, int EDGE, int K> struct MarchConsumer {
         }
         // outputs of row rk = t-2(K-1): T_{i+K-1} = the value step K produced, T_{i+K-2} = the centre of stage K-1
         const int rk = t - 2 * (K - 1);
-        if (emit_col && rk >= j0 && rk < j1) {
+        if (emit_col && (STEADY || (rk >= j0 && rk < j1))) {
             if (!LAST) {
                 P->t1_out.p[o1] = tn[K - 1];
                 P->t2_out.p[o2] = raw[K - 1][(PH - 2 * (K - 1)) & 7];
@@ -220,9 +224,9 @@ template <typename T, int EDGE, int K> struct MarchConsumer {
         // t-2K+1 was last used as the south faces of step K's row
         __syncwarp();
         if (lane0) {
-            if (ti <= last_idx) mbar_arrive(&emptyS[TI0 & 7]);
+            if (STEADY || ti <= last_idx) mbar_arrive(&emptyS[TI0 & 7]);
             const int ci = ti - 2 * K + 1;
-            if (ci >= 0 && ci <= last_idx) mbar_arrive(&emptyC[ci & (MARCH_DC - 1)]);
+            if (STEADY || (ci >= 0 && ci <= last_idx)) mbar_arrive(&emptyC[ci & (MARCH_DC - 1)]);
         }
         named_barrier(1 + l, MARCH_W);
     }
@@ -333,16 +337,27 @@ __global__ void __launch_bounds__(MarchGeom<T>::NTHREADS, 1)
     // function of the phase, so the row windows of the pipeline rotate by renaming instead of by register moves.
     const int t0 = j0 - (K - 1), t1 = j1 - 1 + 2 * (K - 1);
     for (int t = t0, g = 0; t <= t1; t += 8, ++g) {
-        // (iterations beyond t1 in the last trip are no-ops: every wait, step, store and release below is guarded by
-        // its row range, so the trip needs no per-iteration branch)
-        cs.template iteration<0>(t, g);
-        cs.template iteration<1>(t + 1, g);
-        cs.template iteration<2>(t + 2, g);
-        cs.template iteration<3>(t + 3, g);
-        cs.template iteration<4>(t + 4, g);
-        cs.template iteration<5>(t + 5, g);
-        cs.template iteration<6>(t + 6, g);
-        cs.template iteration<7>(t + 7, g);
+        if (t >= j0 + 2 * (K - 1) && t + 7 <= j1 - 1) {  // a trip inside the band: the lean form
+            cs.template iteration<0, true>(t, g);
+            cs.template iteration<1, true>(t + 1, g);
+            cs.template iteration<2, true>(t + 2, g);
+            cs.template iteration<3, true>(t + 3, g);
+            cs.template iteration<4, true>(t + 4, g);
+            cs.template iteration<5, true>(t + 5, g);
+            cs.template iteration<6, true>(t + 6, g);
+            cs.template iteration<7, true>(t + 7, g);
+        } else {
+            // priming / draining trips (iterations beyond t1 in the last one are no-ops: every wait, step, store and
+            // release is guarded by its row range, so a trip needs no per-iteration branch)
+            cs.template iteration<0, false>(t, g);
+            cs.template iteration<1, false>(t + 1, g);
+            cs.template iteration<2, false>(t + 2, g);
+            cs.template iteration<3, false>(t + 3, g);
+            cs.template iteration<4, false>(t + 4, g);
+            cs.template iteration<5, false>(t + 5, g);
+            cs.template iteration<6, false>(t + 6, g);
+            cs.template iteration<7, false>(t + 7, g);
+        }
     }
 }
 #endif
