@@ -149,7 +149,7 @@ template <typename T, int EDGE, int K> struct MarchConsumer {
         named_barrier(1 + l, MARCH_W);
     }
 
-    // iteration t = t0 + 8 g + PH.  STEADY: the caller guarantees j0 + 2(K-1) <= t <= j1 - 1 -- every staged row exists,
+    // iteration t = t0 + 8 g + PH.  STEADY: the caller guarantees j0 + 2(K-1) <= t <= min(j1 - 1, j1 + K - 3) -- every staged row exists,
     // every step is active, the output row is owned -- so none of the (CTA-uniform) range checks below is compiled in:
     // 50 of the 224 instructions of a generic iteration are those checks, their branches and the zeroing / selects of the
     // values they guard.
@@ -337,7 +337,10 @@ __global__ void __launch_bounds__(MarchGeom<T>::NTHREADS, 1)
     // function of the phase, so the row windows of the pipeline rotate by renaming instead of by register moves.
     const int t0 = j0 - (K - 1), t1 = j1 - 1 + 2 * (K - 1);
     for (int t = t0, g = 0; t <= t1; t += 8, ++g) {
-        if (t >= j0 + 2 * (K - 1) && t + 7 <= j1 - 1) {  // a trip inside the band: the lean form
+        // a trip inside the band takes the lean form: all eight iterations satisfy j0 + 2(K-1) <= t <= j1 - 1 and
+        // t + 2 <= j1 + K - 1 (the row staged two ahead exists: binding for K = 1) -- tests/test_march_schedule.py
+        // re-derives every guard that STEADY drops from these bounds
+        if (t >= j0 + 2 * (K - 1) && t + 7 <= j1 - 1 && t + 7 <= j1 + K - 3) {
             cs.template iteration<0, true>(t, g);
             cs.template iteration<1, true>(t + 1, g);
             cs.template iteration<2, true>(t + 2, g);
