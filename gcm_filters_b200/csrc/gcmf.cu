@@ -1328,8 +1328,10 @@ template <typename T> static int launch_march(const gcmf_plan* pl, const FusedPa
 // plane 16-byte aligned.  Forcing a one-step C-grid kernel form with GCMF_CGRID_KERNEL (A/B, tests) switches it off.
 template <typename T> static bool cg2_eligible_t(const gcmf_plan* p) {
 #ifdef GCMF_HOSTEMU
-    (void)p;
-    return false;  // mbarriers + TMA: device only; the emulator runs the one-step kernels (bit-identical by construction)
+    // mbarriers + TMA are device-only: the emulator runs a block as its two one-step launches (bit-identical by
+    // construction), on whole periodic grids, so that the CPU suite covers the blocked control flow of gcmf_filter
+    return (p->desc.op == GCMF_OP_VECTOR_C || p->desc.op == GCMF_OP_VECTOR_B) && (p->desc.flags & GCMF_FLAG_WRAP_Y) &&
+           p->desc.ny >= 4;
 #else
     using G = Cg2Geom<T>;
     static const bool forced = getenv("GCMF_CGRID_KERNEL") != nullptr;
@@ -1416,8 +1418,23 @@ static int run_cg2_t(const gcmf_plan* pl, int64_t nb, int step0, const gcmf_fiel
                      const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st,
                      const gcmf_halo* halo1 = nullptr, const gcmf_halo* halo2 = nullptr) {
 #ifdef GCMF_HOSTEMU
-    (void)pl; (void)nb; (void)step0; (void)t1; (void)t2; (void)t1o; (void)t2o; (void)bar; (void)st; (void)halo1; (void)halo2;
-    return gcmf_set_error(GCMF_EINVAL, "the two-step C-grid kernel is device-only");
+    if (halo1 || halo2) return gcmf_set_error(GCMF_EINVAL, "the exchange fused into the two-step kernel is device-only");
+    // T_i passes through t2_out, or through a scratch copy when the block ends the recurrence (no T is stored then)
+    const bool first = step0 == 1, last = step0 + 1 == pl->n_steps;
+    const int64_t plane = (int64_t)pl->desc.ny * pl->desc.nx;
+    std::vector<T> scratch;
+    gcmf_field tmp[2];
+    const gcmf_field* ti = t2o;
+    if (last) {
+        scratch.resize((size_t)(2 * nb * plane));
+        for (int k = 0; k < 2; ++k) tmp[k] = gcmf_field{scratch.data() + (size_t)k * nb * plane, pl->desc.nx, plane};
+        ti = tmp;
+    }
+    int rc = run_step_t<T>(pl, nb, first ? MODE_FIRST : MODE_MID, t1, first ? nullptr : t2, ti, bar, pl->p[0], pl->p[step0], st);
+    if (rc != GCMF_OK) return rc;
+    rc = run_step_t<T>(pl, nb, last ? MODE_LAST : MODE_MID, ti, t1, last ? nullptr : t1o, bar, pl->p[0], pl->p[step0 + 1], st);
+    gcmf_count_launch(-1);  // one launch on the device
+    return rc;
 #else
     using G = Cg2Geom<T>;
     const bool first = step0 == 1, last = step0 + 1 == pl->n_steps;

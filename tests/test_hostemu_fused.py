@@ -156,3 +156,36 @@ def test_fused_level_slabs(g, dtype, levels, monkeypatch):
         assert np.array_equal(np.isnan(a), np.isnan(b)) and rel_l2(a, b) < 1e-14
     else:
         assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("g", ["VECTOR_C_GRID", "VECTOR_B_GRID"])
+@pytest.mark.parametrize("shape,nb,n_steps", [((40, 64), 2, 6), ((21, 30), 1, 7), ((36, 50), 3, 3)])
+def test_vector_two_step_blocks_equal_one_step(g, shape, nb, n_steps):
+    """The blocked control flow of the vector recurrence (gcmf_filter -> gcmf_cheb_fused with k = 2 on four ping-ponging
+    workspace fields, a trailing one-step launch for odd step counts) through the emulator, which runs a block as its
+    two one-step launches: identical bits, half the launches (the device kernel is pinned against the same one-step
+    kernels by the GPU suite)."""
+    (u, v), gv = fixtures.fixture(g, shape)
+    us = np.stack([u * (1 + 0.1 * k) for k in range(nb)])
+    vs = np.stack([v - 0.2 * k * u for k in range(nb)])
+    us[0, 3:5, 7:9] = np.nan
+    lap = ALL_KERNELS[GridType[g]](**gv)
+    kx, ky = ("dxT", "dyT") if g == "VECTOR_C_GRID" else ("DXU", "DYU")
+    dxm = float(min(gv[kx].min(), gv[ky].min()))
+    spec = _compute_filter_spec(6.0 * dxm, dxm, FilterShape.GAUSSIAN, np.pi, 2, n_steps)
+    c = _shift_scale(spec, lap)
+    blocked = EmuPlan(lap, np.float64, *shape)
+    assert blocked.lib.fused_max_steps(blocked.h) == 2
+    n0 = blocked.lib.launch_count()
+    a = blocked.filter((us, vs), spec.p, c)
+    assert blocked.lib.launch_count() - n0 == (n_steps + 1) // 2
+    plain = EmuPlan(lap, np.float64, *shape)
+    emu_set_steps_per_block(plain, 1)
+    n0 = plain.lib.launch_count()
+    b = plain.filter((us, vs), spec.p, c)
+    assert plain.lib.launch_count() - n0 == n_steps
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
+    ref = np_oracle.run_recurrence(np_oracle.make_operator(g, gv), np_oracle.FilterSpec(*spec), (us, vs))
+    for x, r in zip(a, ref):
+        assert rel_l2(x, r) < 1e-12
