@@ -18,7 +18,7 @@ cap() {  # tag kernel-regex skip "bench args" [extra ncu args]
 cap march_flux_cfg3 march_kernel 15 "--workload cfg3" "--import-source on" keep
 ncu -i gpurun_out/ncu_march_flux_cfg3.ncu-rep --page source --csv > gpurun_out/ncu_march_flux_cfg3.source.csv 2>/dev/null
 rm -f gpurun_out/ncu_march_flux_cfg3.ncu-rep
-GCMF_FUSED_FORM=tile cap fused_flux_tile_cfg3 fused_kernel 15 "--workload cfg3"
+( export GCMF_FUSED_FORM=tile; cap fused_flux_tile_cfg3 fused_kernel 15 "--workload cfg3" )
 cap fused_reg5_f32_cfg2 fused_kernel 4 "--workload cfg2"
 cap fused_flux_tripolar_cfg4 fused_kernel 15 "--workload cfg4 --nb 8"
 cap vec2_cgrid_cfg5 vec2_kernel 12 "--workload cfg5"
