@@ -1329,9 +1329,8 @@ template <typename T> static int launch_march(const gcmf_plan* pl, const FusedPa
 template <typename T> static bool cg2_eligible_t(const gcmf_plan* p) {
 #ifdef GCMF_HOSTEMU
     // mbarriers + TMA are device-only: the emulator runs a block as its two one-step launches (bit-identical by
-    // construction), on whole periodic grids, so that the CPU suite covers the blocked control flow of gcmf_filter
-    return (p->desc.op == GCMF_OP_VECTOR_C || p->desc.op == GCMF_OP_VECTOR_B) && (p->desc.flags & GCMF_FLAG_WRAP_Y) &&
-           p->desc.ny >= 4;
+    // construction), so that the CPU suite covers the blocked control flow of gcmf_filter and of the band scheduler
+    return (p->desc.op == GCMF_OP_VECTOR_C || p->desc.op == GCMF_OP_VECTOR_B) && p->desc.ny >= 4;
 #else
     using G = Cg2Geom<T>;
     static const bool forced = getenv("GCMF_CGRID_KERNEL") != nullptr;
@@ -1429,6 +1428,45 @@ static int run_cg2_t(const gcmf_plan* pl, int64_t nb, int step0, const gcmf_fiel
         scratch.resize((size_t)(2 * nb * plane));
         for (int k = 0; k < 2; ++k) tmp[k] = gcmf_field{scratch.data() + (size_t)k * nb * plane, pl->desc.nx, plane};
         ti = tmp;
+    }
+    if (!(pl->desc.flags & GCMF_FLAG_WRAP_Y)) {
+        // Latitude band (two ghost rows per side present in memory): step i+1 needs T_i on rows -1 .. ny too, so step i
+        // runs on the band extended by one row on either side -- a copy of the plan with ny + 2 rows whose planes and
+        // fields start one row further south -- into scratch arrays with room for those rows.
+        const int ny = pl->desc.ny, nx = pl->desc.nx;
+        const int64_t eplane = (int64_t)(ny + 2) * nx;
+        std::vector<T> Ti((size_t)(2 * nb * eplane)), Be((size_t)(2 * nb * eplane));
+        gcmf_plan ext = *pl;
+        ext.desc.ny = ny + 2;
+        for (int s2 = 0; s2 < ext.n_planes; ++s2)
+            if (ext.plane[s2].p) ext.plane[s2].p = (const T*)ext.plane[s2].p - ext.plane[s2].pitch;
+        gcmf_field e1[2], e2[2], tif[2], bef[2], ti1[2];
+        for (int k = 0; k < 2; ++k) {
+            e1[k] = gcmf_field{(T*)t1[k].ptr - t1[k].pitch, t1[k].pitch, t1[k].bstride};
+            if (!first) e2[k] = gcmf_field{(T*)t2[k].ptr - t2[k].pitch, t2[k].pitch, t2[k].bstride};
+            tif[k] = gcmf_field{Ti.data() + (size_t)k * nb * eplane, nx, eplane};
+            bef[k] = gcmf_field{Be.data() + (size_t)k * nb * eplane, nx, eplane};
+            ti1[k] = gcmf_field{Ti.data() + (size_t)k * nb * eplane + nx, nx, eplane};  // row 0 of the band
+            if (!first)
+                for (int64_t b = 0; b < nb; ++b)
+                    for (int j = 0; j < ny; ++j)
+                        memcpy((T*)bef[k].ptr + b * eplane + (int64_t)(j + 1) * nx,
+                               (const T*)bar[k].ptr + b * bar[k].bstride + (int64_t)j * bar[k].pitch, (size_t)nx * sizeof(T));
+        }
+        int rc = run_step_t<T>(&ext, nb, first ? MODE_FIRST : MODE_MID, e1, first ? nullptr : e2, tif, bef, pl->p[0], pl->p[step0], st);
+        if (rc != GCMF_OK) return rc;
+        for (int k = 0; k < 2; ++k)
+            for (int64_t b = 0; b < nb; ++b)
+                for (int j = 0; j < ny; ++j) {
+                    memcpy((T*)bar[k].ptr + b * bar[k].bstride + (int64_t)j * bar[k].pitch,
+                           (const T*)bef[k].ptr + b * eplane + (int64_t)(j + 1) * nx, (size_t)nx * sizeof(T));
+                    if (!last)
+                        memcpy((T*)t2o[k].ptr + b * t2o[k].bstride + (int64_t)j * t2o[k].pitch,
+                               (const T*)ti1[k].ptr + b * eplane + (int64_t)j * nx, (size_t)nx * sizeof(T));
+                }
+        rc = run_step_t<T>(pl, nb, last ? MODE_LAST : MODE_MID, ti1, t1, last ? nullptr : t1o, bar, pl->p[0], pl->p[step0 + 1], st);
+        gcmf_count_launch(-1);  // one launch on the device
+        return rc;
     }
     int rc = run_step_t<T>(pl, nb, first ? MODE_FIRST : MODE_MID, t1, first ? nullptr : t2, ti, bar, pl->p[0], pl->p[step0], st);
     if (rc != GCMF_OK) return rc;

@@ -157,3 +157,50 @@ def test_fused_band_decomposition(g, dtype, tol, world):
     res = sorted(q.get(timeout=10) for _ in range(world))
     assert [(r[1], r[2]) for r in res] == band_rows(shape[0], world)
     assert max(r[3] for r in res) < tol
+
+
+def _fused_vector_band_worker(rank, world, port, g, shape, scale, q):
+    from gcm_filters_b200.scheduler import FusedBandedFilter
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        (u, v), gv = fixtures.fixture(g, shape)
+        fields = (np.stack([u, u * v]), np.stack([v, 1 - u]))  # two batch slices per component
+        fa = _vec_args(g, gv, dict(filter_scale=scale, dx_min=1.0))
+        flt = Filter(grid_type=GridType[g], grid_vars=gv, filter_shape=FilterShape.GAUSSIAN, **fa)
+        bf = FusedBandedFilter(flt, rank, world, library=emu_library(), device="cpu")
+        for _ in range(2):
+            outs, (j0, j1) = bf.apply(*fields)
+        ref = np_oracle.apply_filter(g, gv, fields, **fa)
+        err = 0.0
+        for o, r in zip(outs, ref):
+            rb = r[..., j0:j1, :]
+            err = max(err, float(np.linalg.norm(o - rb) / np.linalg.norm(rb)))
+        q.put((rank, j0, j1, err, int(flt.n_steps)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("g", ["VECTOR_C_GRID", "VECTOR_B_GRID"])
+@pytest.mark.parametrize("world,scale", [(2, 6.0), (3, 7.0)])
+def test_fused_band_decomposition_vector(g, world, scale):
+    """Two-step blocks of the vector operators on latitude bands: 2 ghost rows per side of the fields and of every
+    coefficient plane, one exchange of the ghost rows of T_{i+1} and T_i per block, a trailing one-step launch when the
+    step count is odd (scale 6: 7 steps, scale 7: 8).  The emulator runs a block on a band as step i on the band extended
+    by one row per side followed by step i+1 on the band -- the data flow of the device kernel."""
+    emu_library()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    shape = (45, 40)
+    procs = [ctx.Process(target=_fused_vector_band_worker, args=(r, world, port, g, shape, scale, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(world))
+    assert [(r[1], r[2]) for r in res] == band_rows(shape[0], world)
+    assert res[0][4] == (7 if scale == 6.0 else 8)
+    assert max(r[3] for r in res) < 1e-12
