@@ -1417,7 +1417,6 @@ static int run_cg2_t(const gcmf_plan* pl, int64_t nb, int step0, const gcmf_fiel
                      const gcmf_field* t1o, const gcmf_field* t2o, const gcmf_field* bar, cudaStream_t st,
                      const gcmf_halo* halo1 = nullptr, const gcmf_halo* halo2 = nullptr) {
 #ifdef GCMF_HOSTEMU
-    if (halo1 || halo2) return gcmf_set_error(GCMF_EINVAL, "the exchange fused into the two-step kernel is device-only");
     // T_i passes through t2_out, or through a scratch copy when the block ends the recurrence (no T is stored then)
     const bool first = step0 == 1, last = step0 + 1 == pl->n_steps;
     const int64_t plane = (int64_t)pl->desc.ny * pl->desc.nx;
@@ -1466,8 +1465,28 @@ static int run_cg2_t(const gcmf_plan* pl, int64_t nb, int step0, const gcmf_fiel
                 }
         rc = run_step_t<T>(pl, nb, last ? MODE_LAST : MODE_MID, ti1, t1, last ? nullptr : t1o, bar, pl->p[0], pl->p[step0 + 1], st);
         gcmf_count_launch(-1);  // one launch on the device
+        if (rc == GCMF_OK && halo1) {
+            // the exchange fused into the device kernel: the emulator has no concurrency, so the border rows are copied
+            // into the "neighbours'" ghost rows after the block and the flags raised (as for gcmf_cheb_step_halo)
+            const gcmf_halo* hs[2] = {halo1, halo2 ? halo2 : halo1};
+            const gcmf_field* outs[2] = {t1o, t2o};
+            for (int a = 0; a < 2 && !last; ++a)
+                for (int k = 0; k < 2; ++k)
+                    for (int64_t b = 0; b < nb; ++b)
+                        for (int r = 0; r < 2; ++r) {
+                            const T* src_s = (const T*)outs[a][k].ptr + b * outs[a][k].bstride + (int64_t)r * outs[a][k].pitch;
+                            const T* src_n = (const T*)outs[a][k].ptr + b * outs[a][k].bstride + (int64_t)(ny - 2 + r) * outs[a][k].pitch;
+                            if (hs[a]->south_ghost[k])
+                                memcpy((T*)hs[a]->south_ghost[k] + b * hs[a]->south_bstride + (int64_t)r * outs[a][k].pitch, src_s, (size_t)nx * sizeof(T));
+                            if (hs[a]->north_ghost[k])
+                                memcpy((T*)hs[a]->north_ghost[k] + b * hs[a]->north_bstride + (int64_t)r * outs[a][k].pitch, src_n, (size_t)nx * sizeof(T));
+                        }
+            if (halo1->signal_north) *halo1->signal_north = halo1->signal_value;
+            if (halo1->signal_south) *halo1->signal_south = halo1->signal_value;
+        }
         return rc;
     }
+    if (halo1) return gcmf_set_error(GCMF_EINVAL, "halo exchange needs a band plan (no GCMF_FLAG_WRAP_Y)");
     int rc = run_step_t<T>(pl, nb, first ? MODE_FIRST : MODE_MID, t1, first ? nullptr : t2, ti, bar, pl->p[0], pl->p[step0], st);
     if (rc != GCMF_OK) return rc;
     rc = run_step_t<T>(pl, nb, last ? MODE_LAST : MODE_MID, ti, t1, last ? nullptr : t1o, bar, pl->p[0], pl->p[step0 + 1], st);

@@ -200,3 +200,37 @@ def test_peer_banded_filter_single_rank(g, shape):
     ref = ref if isinstance(ref, tuple) else (ref,)
     for o, r in zip(outs, ref):
         assert rel_l2(o, r) < 1e-12
+
+
+@pytest.mark.parametrize("shape,scale", [((41, 48), 6.0), ((24, 36), 7.0), ((9, 20), 6.0)])
+@pytest.mark.parametrize("g", ["VECTOR_C_GRID", "VECTOR_B_GRID"])
+def test_fused_banded_push_single_rank(g, shape, scale):
+    """FusedBandedFilter(exchange="push") -- gcmf_cheb_fused_halo: two-step blocks whose border rows of T_{i+1} and T_i
+    go straight into the neighbours' ghost rows -- with one rank that is its own north and south neighbour, buffers in
+    ordinary memory: the host side of the protocol (addresses of the two ghost rows per side in the six rotating arrays,
+    flag words behind them, growing flag values over several runs on one staging, the trailing one-step launch of an
+    odd step count) against the oracle.  The emulator copies the border rows and raises the flags after each block;
+    the device kernel and the multi-GPU protocol are tests/test_gpu_parity.py / tests/test_gpu_multi.py."""
+    from gcm_filters_b200 import Filter, FilterShape
+    from gcm_filters_b200.scheduler import FusedBandedFilter
+    from hostemu_util import emu_library
+    fields, gv = fixtures.fixture(g, shape)
+    fields = tuple(np.stack([f, 1.0 - f * f]) for f in fields)
+    kx, ky = ("dxT", "dyT") if g == "VECTOR_C_GRID" else ("DXU", "DYU")
+    dxm = float(min(gv[kx].min(), gv[ky].min()))
+    fa = dict(filter_scale=scale * dxm, dx_min=dxm)
+    flt = Filter(grid_type=GridType[g], grid_vars=gv, filter_shape=FilterShape.GAUSSIAN, **fa)
+    assert flt.n_steps == (7 if scale == 6.0 else 8)
+    fbf = FusedBandedFilter(flt, 0, 1, library=emu_library(), device="cpu", exchange="push")
+    assert fbf.exchange == "push"
+    st = fbf.stage(*fields)
+    for _ in range(3):
+        bar = fbf.run(st)
+    ref = np_oracle.apply_filter(g, gv, fields, **fa)
+    for k, r in enumerate(ref):
+        assert rel_l2(bar[k].numpy(), r) < 1e-12
+    # the same through apply() (fresh staging, flags restart)
+    outs, (j0, j1) = fbf.apply(*fields)
+    assert (j0, j1) == (0, shape[0])
+    for o, r in zip(outs, ref):
+        assert rel_l2(o, r) < 1e-12
