@@ -22,7 +22,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 BAND_GRIDS = ["IRREGULAR_WITH_LAND", "TRIPOLAR_POP_WITH_LAND", "VECTOR_C_GRID", "VECTOR_B_GRID", "MOM5U", "REGULAR",
               "REGULAR_WITH_LAND_AREA_WEIGHTED", "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED", "REGULAR_WITH_LAND"]
 FUSED_GRIDS = ["IRREGULAR_WITH_LAND", "REGULAR_WITH_LAND", "REGULAR_WITH_LAND_AREA_WEIGHTED", "TRIPOLAR_POP_WITH_LAND",
-               "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED", "MOM5T", "REGULAR"]
+               "TRIPOLAR_REGULAR_WITH_LAND_AREA_WEIGHTED", "MOM5T", "REGULAR", "VECTOR_C_GRID", "VECTOR_B_GRID"]
 
 
 def worker(rank, world, port, cases, seed, q):
@@ -46,6 +46,9 @@ def worker(rank, world, port, cases, seed, q):
                 g = FUSED_GRIDS[rng.integers(len(FUSED_GRIDS))]
                 ny = int(rng.integers(32 * world, 48 * world + 16))
                 nx = int(rng.integers(128 if dtype == np.float64 else 256, 330)) // 4 * 4
+                if g.startswith("VECTOR"):  # two-step blocks, two ghost rows: any band of at least four rows (emulator)
+                    ny = int(rng.integers(4 * world, 30 * world))
+                    nx = int(rng.integers(8, 80))
             else:
                 g = BAND_GRIDS[rng.integers(len(BAND_GRIDS))]
                 ny = int(rng.integers(4 * world, 30 * world))
