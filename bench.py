@@ -559,7 +559,7 @@ def measure(ctx, args, name, nb=0, primary=False):
               f"vec2_kernel ({dom[1]} Chebyshev steps per launch, rows streamed through TMA rings)"
               if ncomp == 2 else
               f"march_kernel ({dom[1]} Chebyshev steps per launch, rows streamed through TMA rings, row windows in registers)"
-              if (cfg["grid_type"] in ("IRREGULAR_WITH_LAND", "MOM5U", "MOM5T") and w == 8 and nbl >= 3 and nbl != 4
+              if (cfg["grid_type"] in ("IRREGULAR_WITH_LAND", "MOM5U", "MOM5T") and w == 8 and nbl >= 2
                   and os.environ.get("GCMF_FUSED_FORM") != "tile") else
               f"fused_kernel ({dom[1]} Chebyshev steps per launch, TMA-staged tiles)")
         kname = {"fused": fk, "fused_first": fk + ", first block", "fused_last": fk + ", last block",

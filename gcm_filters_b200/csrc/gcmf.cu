@@ -1262,9 +1262,10 @@ template <typename T> static bool march_eligible(const gcmf_plan* pl, int64_t nb
     if (pl->desc.flags & (GCMF_FLAG_FOLD_N | GCMF_FLAG_CUT_S)) return false;
     if (pl->desc.nx < MARCH_W) return false;
     if (force && !strcmp(force, "march")) return true;  // incl. latitude bands and fp32
-    // a CTA marches MARCH_LV = 3 levels at once (3.8 ms per group of three on the cfg3 grid, against 1.6 - 2.3 ms per level
-    // of the tile form): batches of 1, 2 or 4 levels leave too many of its level slots empty
-    return sizeof(T) == 8 && (pl->desc.flags & GCMF_FLAG_WRAP_Y) != 0 && nb >= 3 && nb != 4;
+    // a CTA marches MARCH_LV levels at once: a single level leaves half of its level slots empty (with three levels per
+    // CTA: 1, 2 and 4 levels)
+    if (sizeof(T) != 8 || !(pl->desc.flags & GCMF_FLAG_WRAP_Y)) return false;
+    return MARCH_LV == 2 ? nb >= 2 : (nb >= 3 && nb != 4);
 }
 
 template <typename T, int EDGE, int K> static int launch_march_t(const gcmf_plan* pl, const FusedParams<T>& P, cudaStream_t st) {
@@ -1279,7 +1280,7 @@ template <typename T, int EDGE, int K> static int launch_march_t(const gcmf_plan
     }
     const int nstrips = (P.g.nx + G::SW - 1) / G::SW;
     const int nlg = (int)((P.nb + MARCH_LV - 1) / MARCH_LV);
-    // Rows per band: 3(K-1) priming iterations per band against enough CTAs for nine rounds of the device (the tail of
+    // Rows per band (the sweeps below: three levels per CTA): 3(K-1) priming iterations per band against enough CTAs for nine rounds of the device (the tail of
     // a launch is one CTA long): the tallest band of at most 400 rows that leaves that many.  Measured on cfg3, ms per
     // filter call: nb = 62 (630 CTAs per band): 200 rows 82.3, 400: 80.5, 800: 81.6 (before the steady-state
     // iterations: 60: 95.5, 120: 89.1, 240: 85.4, 400: 84.7, 600: 84.9, 1200: 86.9, 2400: 98.8); nb = 8 (90 CTAs per

@@ -24,12 +24,11 @@
 //   * rows of T_{i-1}, T_{i-2}, bar of the LV levels (8-slot ring) and of the three coefficient planes, shared by the
 //     levels (16-slot ring: a coefficient row stays in use for 2K iterations), are streamed by the TMA engine (one lane
 //     per array, cp.async.bulk -> UBLKCP, mbarrier complete_tx) several rows ahead by a dedicated producer warp.
-//     (MARCH_LV = 3: with four levels the producer would be a 17th warp, five warps on one of the four register-file
-//     sub-partitions, which caps every thread at 96 registers and spills; folding the producer duty into consumer
-//     warp 0 instead made the whole CTA run at that warp's pace -- measured 1.3x to 2x slower than the tile form.)
+//     (Folding the producer duty into consumer warp 0 made the whole CTA run at that warp's pace -- measured 1.3x to
+//     2x slower than the tile form.  MARCH_LV below: two levels per CTA and two CTAs per SM beat three levels and one.)
 //
-// HBM traffic per grid-point step: (6w + 3w/LV) / K * (128/120) = 14.4 B (fp64, K = 4) plus 3(K-1) priming iterations
-// per band; measured 12.8 B (ncu, 400-row bands; the halo columns hit in L2).  All 12 consumer warps do the same work;
+// HBM traffic per grid-point step: (6w + 3w/LV) / K * (128/120) = 14.4 B (fp64, K = 4, LV = 3; 16 B at LV = 2) plus 3(K-1)
+// priming iterations per band; measured 13.0 B at LV = 3 (ncu, 400-row bands; the halo columns hit in L2).  All consumer warps do the same work;
 // the per-step shared-memory traffic is 7 LDS.64 + 1 STS.64 per point instead of a full tile sweep.
 //
 // The arithmetic of a point is the same inline code as everywhere else (flux_lap, shifted_flux, cheb_next,
@@ -40,8 +39,16 @@
 
 namespace gcmf {
 
+// Levels per CTA.  2 (default): 8 consumer warps + the producer warp, 115 KB of shared memory, TWO CTAs per SM = 16
+// consumer warps per SM at 96 registers per thread (60 - 90 bytes of spills).  3: 12 consumer warps, one CTA per SM, 128
+// registers, no spills.  Measured on cfg3 (ms per filter call, bit-identical results): nb = 62: 72.7 vs 80.6, nb = 8:
+// 10.6 vs 12.2 -- the kernel is bound by fixed-latency fp64 dependencies, so warps per scheduler matter more than the
+// spills and than sharing a coefficient row among three levels instead of two.
 #ifndef GCMF_MARCH_LV
-#define GCMF_MARCH_LV 3  // 12 consumer warps + the producer warp = 13 warps: at most 4 on a sub-partition, 128 registers
+#define GCMF_MARCH_LV 2
+#endif
+#ifndef GCMF_MARCH_MINCTAS
+#define GCMF_MARCH_MINCTAS (GCMF_MARCH_LV == 2 ? 2 : 1)
 #endif
 constexpr int MARCH_LV = GCMF_MARCH_LV;  // levels per CTA (they share the coefficient rows)
 constexpr int MARCH_W = 128;             // threads per level = staged columns per row
@@ -235,7 +242,7 @@ template <typename T, int EDGE, int K> struct MarchConsumer {
 // EDGE as in fused_kernel: bit 0 = the block starts at recurrence step 1, bit 1 = it ends at step n_steps.
 // K = steps of the block (compile time: the step loop is straight-line code).
 template <typename T, int EDGE, int K>
-__global__ void __launch_bounds__(MarchGeom<T>::NTHREADS, 1)
+__global__ void __launch_bounds__(MarchGeom<T>::NTHREADS, GCMF_MARCH_MINCTAS)
     march_kernel(const __grid_constant__ FusedParams<T> P, int nstrips, int nlg, int ry) {
     using G = MarchGeom<T>;
     constexpr bool FIRST = (EDGE & 1) != 0, LAST = (EDGE & 2) != 0;

@@ -341,19 +341,21 @@ def _host_view(f, nb, ny, nx):
     return torch.from_numpy(a.reshape((nb, ny, nx)))
 
 
-PIPELINE_LEVEL_GROUP = 3  # the row-streaming kernel marches three batch slices per CTA (gcmf_march.cuh: MARCH_LV)
+PIPELINE_LEVEL_GROUP = 2  # the row-streaming kernel marches two batch slices per CTA (gcmf_march.cuh: MARCH_LV)
 
 
 def _pipeline_chunk(nb, slice_bytes):
     """Batch slices per pipeline chunk: about nb / PIPELINE_TARGET_CHUNKS, capped in bytes, and a multiple of the level
-    group of the row-streaming kernel when it is at least one group (a chunk of 7 slices occupies three groups, i.e. 7 of
-    9 level slots: measured 1.67 ms per slice on the cfg3 grid against 1.33 ms for chunks of 6)."""
+    group of the row-streaming kernel when it is at least one group (measured with three levels per CTA on the cfg3 grid:
+    a chunk of 7 slices, 7 of 9 level slots, costs 1.67 ms per slice against 1.33 ms for chunks of 6: e2e 199.5 -> 221.5 G)."""
     chunk = max(1, nb // PIPELINE_TARGET_CHUNKS)
     chunk = min(chunk, max(1, PIPELINE_MAX_CHUNK_BYTES // max(1, slice_bytes)))
     if chunk < PIPELINE_LEVEL_GROUP and nb >= PIPELINE_MIN_CHUNKS * PIPELINE_LEVEL_GROUP:
         chunk = PIPELINE_LEVEL_GROUP  # still at least PIPELINE_MIN_CHUNKS chunks, and every chunk a whole group
     if chunk >= PIPELINE_LEVEL_GROUP:
-        chunk = PIPELINE_LEVEL_GROUP * max(1, int(chunk / PIPELINE_LEVEL_GROUP + 0.5))
+        whole = PIPELINE_LEVEL_GROUP * (chunk // PIPELINE_LEVEL_GROUP)
+        # a whole number of groups: down (more chunks overlap better), except from 3 slices, where down would halve it
+        chunk = whole if whole >= 2 * PIPELINE_LEVEL_GROUP or whole == chunk else whole + PIPELINE_LEVEL_GROUP
         while chunk > PIPELINE_LEVEL_GROUP and chunk * slice_bytes > PIPELINE_MAX_CHUNK_BYTES:
             chunk -= PIPELINE_LEVEL_GROUP
     return chunk

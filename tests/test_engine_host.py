@@ -16,12 +16,13 @@ def test_chunk_schedule_covers_the_batch_once(nb, chunk):
 
 
 def test_pipeline_chunk_is_bounded_by_bytes_and_target():
-    assert engine.PIPELINE_TARGET_CHUNKS == 8 and engine.PIPELINE_LEVEL_GROUP == 3
-    assert engine._pipeline_chunk(62, 2400 * 3600 * 8) == 6   # 62 // 8 = 7 -> the nearest multiple of the level group
-    assert engine._pipeline_chunk(365, 720 * 1440 * 4) == 45  # already a multiple
-    assert engine._pipeline_chunk(37, 64 * 160 * 8) == 3 and engine._pipeline_chunk(16, 1000) == 3
-    assert engine._pipeline_chunk(11, 1000) == 1              # too short for four whole groups
-    assert engine._pipeline_chunk(400, 200 << 20) == 3        # the byte cap (1 GiB) wins: 5 slices fit, one group is kept
+    assert engine.PIPELINE_TARGET_CHUNKS == 8 and engine.PIPELINE_LEVEL_GROUP == 2
+    assert engine._pipeline_chunk(62, 2400 * 3600 * 8) == 6   # 62 // 8 = 7 -> a whole number of level groups
+    assert engine._pipeline_chunk(365, 720 * 1440 * 4) == 44
+    assert engine._pipeline_chunk(37, 64 * 160 * 8) == 4 and engine._pipeline_chunk(16, 1000) == 2
+    assert engine._pipeline_chunk(11, 1000) == 2              # one group per chunk still leaves four chunks
+    assert engine._pipeline_chunk(7, 1000) == 1               # too short for four whole groups
+    assert engine._pipeline_chunk(400, 200 << 20) == 4        # the byte cap (1 GiB) wins: 5 slices fit
     assert engine._pipeline_chunk(4, 1 << 40) == 1  # a slice larger than the byte cap still moves one at a time
 
 

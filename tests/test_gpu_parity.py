@@ -321,8 +321,8 @@ def test_pipelined_host_path_matches_monolithic():
     fb[:, gv["wet_mask"] == 0] = np.nan
     flt = make_filter("IRREGULAR_WITH_LAND", gv, filter_scale=8.0, dx_min=1.0)
     mono = flt.apply(torch.as_tensor(fb).cuda(), None).cpu().numpy()  # device-resident: never pipelined
-    assert engine._pipeline_chunk(37, 64 * 160 * 8) == 3
-    piped = flt.apply(fb, None)  # numpy in, numpy out: chunks of 1, 1, 3 x 11, 1, 1 slices
+    assert engine._pipeline_chunk(37, 64 * 160 * 8) == 4
+    piped = flt.apply(fb, None)  # numpy in, numpy out: chunks of 1, 2, 4 x 7, 3, 2, 1 slices
     assert isinstance(piped, np.ndarray) and np.array_equal(piped, mono, equal_nan=True)
     pin_in = torch.as_tensor(fb).pin_memory()
     pin_out = torch.empty_like(pin_in).pin_memory()
