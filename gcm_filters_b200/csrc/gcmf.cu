@@ -1251,9 +1251,9 @@ static int launch_fused_kernel(gcmf_plan* pl, const FusedParams<T>& P, int64_t n
 // ---- row-streaming form of the fused FLUX steps (gcmf_march.cuh) ----------------------------------------------
 // The DEFAULT for fp64 FLUX plans on whole doubly periodic grids (cfg3) since its consumer keeps the row windows in
 // row-keyed register slots (gcmf_march.cuh): measured on a B200 against the tile form (profiles/variants_r02c_march.log,
-// ncu_r02c_march8_cfg3.*): cfg3 nb = 62: 80.5 vs 100.9 ms per filter call (293 vs 234 G units/s), nb = 8: 12.3 vs 13.9 ms;
-// 4.1 G warp instructions per 4-step launch against 6.1 G (before the check-free steady-state iterations: fewer still).  The tile form keeps the tripolar grids (the fold), the
-// latitude bands, grids narrower than one strip and fp32 (63.8 vs 77.8 ms on the cfg3 shape: twice the columns per tile
+// variants_r02d_march_lv2.log, ncu_r02d_march_final_cfg3.*): cfg3 nb = 62: 72.7 vs 100.9 ms per filter call (324 vs 234 G
+// units/s), nb = 8: 10.6 vs 13.9 ms.  The tile form keeps the tripolar grids (the fold), the latitude bands, grids
+// narrower than one strip, single-level launches and fp32 (63.8 vs 77.8 ms on the cfg3 shape: twice the columns per tile
 // row).  GCMF_FUSED_FORM=tile|march forces one form where both are eligible (A/B, tests).
 template <typename T> static bool march_eligible(const gcmf_plan* pl, int64_t nb) {
     static const char* force = getenv("GCMF_FUSED_FORM");
