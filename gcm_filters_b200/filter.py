@@ -286,7 +286,8 @@ class Filter:
         ``ds`` may be an ``xarray.DataArray`` / ``xarray.Dataset`` (when xarray is installed; same
         semantics as the reference, filter.py:430-469, dimension order matters: y first), or a
         plain numpy array / torch tensor whose LAST two axes are (y, x); leading axes are batch
-        dimensions.  For arrays ``dims`` is only checked for length."""
+        dimensions.  For arrays ``dims`` is only checked for length.  A ``dict`` of such arrays (several
+        variables on one grid) returns a dict; numpy variables of one dtype share one batched call."""
         if issubclass(self.Laplacian, BaseVectorLaplacian):
             raise ValueError(
                 f"Provided Laplacian {self.Laplacian} is a vector Laplacian. "
@@ -307,7 +308,30 @@ class Filter:
                     stacklevel=2,
                 )
             return filtered
+        if isinstance(ds, dict):
+            return self._apply_to_mapping(ds, dims)
         return self._apply_to_dataarray(ds, dims=dims, out=out)
+
+    def _apply_to_mapping(self, variables, dims):
+        """``{name: array}`` of variables that live on the same horizontal grid (the array counterpart of the reference's
+        Dataset loop, filter.py:454-467): numpy arrays of one dtype are filtered in ONE batched call -- their batch
+        axes are flattened and concatenated, so the coefficient planes are staged once and the launches are as long
+        as for a single large variable -- anything else (device tensors, mixed dtypes) variable by variable."""
+        if not variables:
+            return {}
+        names = list(variables)
+        arrs = [variables[k] for k in names]
+        plain = all(isinstance(a, np.ndarray) and a.ndim >= 2 for a in arrs)
+        if plain and len({a.dtype for a in arrs}) == 1 and len({a.shape[-2:] for a in arrs}) == 1 and len(arrs) > 1:
+            ny, nx = arrs[0].shape[-2:]
+            flat = [a.reshape((-1, ny, nx)) for a in arrs]
+            res = self._apply_to_dataarray(np.concatenate(flat), dims=dims)
+            out, b0 = {}, 0
+            for k, a, f in zip(names, arrs, flat):
+                out[k] = res[b0:b0 + f.shape[0]].reshape(a.shape)
+                b0 += f.shape[0]
+            return out
+        return {k: self._apply_to_dataarray(a, dims=dims) for k, a in zip(names, arrs)}
 
     def _grid_args(self):
         return [self.grid_ds[name] for name in self.Laplacian.required_grid_args()]

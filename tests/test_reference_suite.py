@@ -343,3 +343,22 @@ def test_viscosity_filter(g, backend, xr):
         grid_vars_missing = {k: v for k, v in grid_vars.items() if k != gv}
         with pytest.raises(ValueError, match=r"Provided `grid_vars` .*"):
             Filter(grid_type=grid_type, grid_vars=grid_vars_missing, **filter_args)
+
+
+def test_several_variables_in_one_call(backend):
+    """Beyond the reference: a dict of variables on one grid is the array counterpart of the Dataset loop
+    (reference filter.py:454-467); numpy variables of one dtype share ONE batched filter call (their batch axes are
+    flattened and concatenated) and must equal the variable-by-variable results bit for bit."""
+    grid_type, data, gv = scalar_data("IRREGULAR_WITH_LAND")
+    rng = np.random.default_rng(11)
+    variables = {"temp": data, "salt": np.stack([data * 2.0, 1.0 - data, data * data]),
+                 "age": rng.random((2, 2) + data.shape)}
+    flt = Filter(filter_scale=4.0, dx_min=1.0, grid_type=grid_type, grid_vars=gv)
+    out = flt.apply(variables, dims=["y", "x"])
+    assert set(out) == set(variables)
+    for k, v in variables.items():
+        single = flt.apply(v, dims=["y", "x"])
+        assert out[k].shape == v.shape and np.array_equal(out[k], single, equal_nan=True), k
+    assert flt.apply({}, dims=["y", "x"]) == {}
+    mixed = flt.apply({"a": data, "b": data.astype(np.float32)}, dims=["y", "x"])  # mixed dtypes: one call each
+    assert mixed["a"].dtype == np.float64 and np.array_equal(mixed["a"], flt.apply(data, dims=["y", "x"]), equal_nan=True)
